@@ -1,0 +1,127 @@
+/* b200enc.h — C ABI of the B200-native FFV1 (+FLAC) encode path behind RAWcooked.
+ *
+ * What this boundary replaces.  RAWcooked has no in-process encoder: after analysing the
+ * inputs it builds an `ffmpeg …` command line and runs it with system()
+ * (reference: Source/CLI/Output.cpp:36-378, the system() call is Output.cpp:356; the binary
+ * name comes from --bin-name, Source/CLI/Global.cpp:543-550, default "ffmpeg" :913-914).
+ * The per-frame work ffmpeg does for that command (FFV1 v3 slice encode with RAWcooked's
+ * option set `-coder 1 -context 1 -g 1 -level 3 -slicecrc 1 -slices N`,
+ * Source/CLI/Global.cpp:938-989) is what the entry points below do on a B200.
+ * The bitstream they emit is what the reference's own decoder consumes in `--check`
+ * (Source/Lib/CoDec/FFV1/FFV1_Frame.cpp:134-228, FFV1_Slice.cpp:210-318).
+ *
+ * Conventions: plain C, caller-owned buffers, no exceptions cross the boundary, every
+ * function returns 0 on success or a negative b200_status; b200_last_error() gives text.
+ * There is NO CPU fallback: without a CUDA device every encode entry point fails with
+ * B200_ERR_NO_DEVICE.
+ */
+#ifndef B200ENC_H
+#define B200ENC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200_status {
+    B200_OK = 0,
+    B200_ERR_INVALID = -1,      /* bad argument / unsupported configuration            */
+    B200_ERR_NO_DEVICE = -2,    /* no CUDA device (there is no CPU fallback)           */
+    B200_ERR_CUDA = -3,         /* a CUDA runtime call or a kernel failed              */
+    B200_ERR_OVERFLOW = -4,     /* an output or intermediate buffer was too small      */
+    B200_ERR_IO = -5,           /* file open/read/write failed (CLI entry point)       */
+    B200_ERR_EXISTS = -6        /* output exists and -n was given (CLI entry point)    */
+} b200_status;
+
+/* Source pixel layouts = the image payload of the file exactly as stored on disk.
+ * Values 0..7 equal the reference's dpx::flavor indices
+ * (Source/Lib/Uncompressed/DPX/DPX.h:38-46; byte layouts at Source/Lib/Transform/Transform.cpp:70-420),
+ * 32..34 are tiff::flavor RGB flavors (Source/Lib/Uncompressed/TIFF/TIFF.h:36-40; Transform.cpp:1048-1055). */
+typedef enum b200_layout {
+    B200_DPX_RGB_8              = 0,  /* R,G,B bytes                                              */
+    B200_DPX_RGB_10_FILLED_A_LE = 1,  /* 32-bit word R<<22|G<<12|B<<2, little endian              */
+    B200_DPX_RGB_10_FILLED_A_BE = 2,  /* same word, big endian                                    */
+    B200_DPX_RGB_12_FILLED_A_LE = 3,  /* 3 x 16-bit (v<<4), little endian                         */
+    B200_DPX_RGB_12_PACKED_BE   = 4,  /* 12-bit samples LSB-first in big-endian 32-bit words,     */
+                                      /* each row padded to a 32-bit boundary                     */
+    B200_DPX_RGB_12_FILLED_A_BE = 5,  /* 3 x 16-bit (v<<4), big endian                            */
+    B200_DPX_RGB_16_LE          = 6,  /* 3 x 16-bit little endian                                 */
+    B200_DPX_RGB_16_BE          = 7,  /* 3 x 16-bit big endian                                    */
+    B200_TIFF_RGB_8             = 32, /* R,G,B bytes, rows tightly packed                         */
+    B200_TIFF_RGB_16_LE         = 33,
+    B200_TIFF_RGB_16_BE         = 34
+} b200_layout;
+
+/* Encoder configuration = the subset of ffmpeg's ffv1 options RAWcooked emits
+ * (Source/CLI/Global.cpp:938-989; slices: Source/CLI/Output.cpp:41-57). */
+typedef struct b200_ffv1_cfg {
+    uint32_t width;
+    uint32_t height;
+    int32_t  layout;      /* b200_layout; fixes bits_per_raw_sample (8/10/12/16)                 */
+    int32_t  slices;      /* `-slices N`; 0 = pick like ffmpeg; grid = b200_ffv1_slice_grid()    */
+    int32_t  context;     /* `-context`: 0 small, 1 large context model (RAWcooked default 1)     */
+    int32_t  coder;       /* `-coder`: 1 (range coder; sent as coder_type 2 like ffmpeg) only     */
+    int32_t  slicecrc;    /* `-slicecrc`: 1 (ec = 1, RAWcooked default) or 0                      */
+    int32_t  max_frames;  /* frames per batch the handle must be able to hold in flight (>=1)     */
+    int32_t  device;      /* CUDA device ordinal                                                  */
+    int32_t  reserved[7]; /* must be 0 */
+} b200_ffv1_cfg;
+
+typedef struct b200_ffv1_enc b200_ffv1_enc;
+
+/* `-slices N` -> (num_h_slices, num_v_slices) with ffmpeg's search (the set of
+ * valid counts is pinned by the reference's test/slices.sh:12). Returns B200_ERR_INVALID if N has no grid. */
+int b200_ffv1_slice_grid(uint32_t width, uint32_t height, int32_t slices, int32_t* num_h, int32_t* num_v);
+
+/* Bytes of image payload one frame has in `layout` (what the reference computes at
+ * Source/Lib/Uncompressed/DPX/DPX.cpp:460-483). 0 if unsupported. */
+size_t b200_ffv1_frame_bytes(uint32_t width, uint32_t height, int32_t layout);
+
+/* Create an encoder (allocates all device memory for max_frames frames in flight). */
+int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out);
+void b200_ffv1_close(b200_ffv1_enc* enc);
+
+/* FFV1 ConfigurationRecord = Matroska CodecPrivate of the V_FFV1 track
+ * (what the reference parses at Source/Lib/CoDec/FFV1/FFV1_Parameters.cpp:23-183 after the CRC
+ * check at FFV1_Frame.cpp:114-117). Returns its size; copies min(size, cap) bytes. */
+size_t b200_ffv1_config_record(const b200_ffv1_enc* enc, uint8_t* out, size_t cap);
+
+/* Upper bound of one packet's size, for sizing `out` below. */
+size_t b200_ffv1_max_packet_bytes(const b200_ffv1_enc* enc);
+
+/* Encode `n_frames` (<= max_frames) frames whose payloads lie in HOST memory at frames[i]
+ * (each b200_ffv1_frame_bytes() long). Packets are written back to back into `out`
+ * (host memory, capacity `out_cap`); packet i occupies [out_off[i], out_off[i] + out_len[i]).
+ * One packet = one Matroska SimpleBlock payload (one keyframe, all slices, slice CRCs).
+ * The call includes host->device and device->host copies and is synchronous. */
+int b200_ffv1_encode_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int32_t n_frames,
+                          uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len);
+
+/* Device-resident variant: `d_frames` is ONE device buffer holding n_frames payloads back to back
+ * (stride b200_ffv1_frame_bytes()); packets are produced into an internal device buffer.
+ * `stream` is a cudaStream_t (0 = default stream); the call is asynchronous on it.
+ * After a stream sync, b200_ffv1_packets_device() returns the device pointer of the packet arena and
+ * copies the per-frame offsets/lengths to the host arrays; b200_ffv1_fetch_packets() copies the bytes. */
+int b200_ffv1_encode_device(b200_ffv1_enc* enc, const void* d_frames, int32_t n_frames, void* stream);
+int b200_ffv1_packets_device(b200_ffv1_enc* enc, const void** d_arena, size_t* out_off, size_t* out_len, int32_t n_frames);
+int b200_ffv1_fetch_packets(b200_ffv1_enc* enc, uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len, int32_t n_frames);
+
+/* Counters of the last encode call: [0] kernels launched, [1] range-coder bins coded,
+ * [2] samples coded, [3] bytes of packets produced; plus device time of the dominant kernels in
+ * microseconds when timing is enabled via b200_ffv1_set_timing(): [4] model kernel, [5] coder kernel,
+ * [6] pack kernel. Unused slots are 0. */
+int b200_ffv1_stats(const b200_ffv1_enc* enc, uint64_t stats[8]);
+int b200_ffv1_set_timing(b200_ffv1_enc* enc, int32_t enabled);
+
+/* Text of the last error on this thread ("" if none). */
+const char* b200_last_error(void);
+
+/* Library/ABI version: (major<<16)|(minor<<8)|patch. */
+uint32_t b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ENC_H */

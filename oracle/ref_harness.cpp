@@ -1,0 +1,71 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): packet-level harness around the UNMODIFIED
+// reference FFV1 decoder of MediaArea/RAWcooked. Compiled by oracle/build_ref.sh
+// together with the reference's own sources where they lie under /root/reference
+// (nothing is copied), output goes to oracle/_ref/libref_ffv1dec.so.
+//
+// It drives exactly what `rawcooked --check` drives for one video packet:
+//   ffv1_frame::OutOfBand  (Source/Lib/CoDec/FFV1/FFV1_Frame.cpp:105-131)
+//   ffv1_frame::Process    (Source/Lib/CoDec/FFV1/FFV1_Frame.cpp:134-228)
+//   -> slice::Parse -> Transform->From  (DPX/TIFF byte layout, Transform.cpp)
+// and hands back the bytes of raw_frame plane 0, i.e. the image payload of the
+// DPX/TIFF file the packet must reproduce.
+#include "Lib/CoDec/FFV1/FFV1_Frame.h"
+#include "Lib/Utils/RawFrame/RawFrame.h"
+#include "Lib/Utils/CRC32/ZenCRC32.h"
+#include "ThreadPool.h"
+#include <cstring>
+#include <cstdio>
+
+extern "C" {
+
+// container: 0 = DPX (flavor = dpx::flavor index, DPX.h:38-61), 1 = TIFF (tiff::flavor, TIFF.h:36-45)
+// returns 0 on success, 1 if the reference decoder flagged an error (message in err), 2 on size problems
+int ref_ffv1_decode(const uint8_t* extradata, size_t extradata_size,
+                    uint32_t width, uint32_t height, int container, int flavor,
+                    const uint8_t* pkt, size_t pkt_size,
+                    uint8_t* out, size_t out_cap, size_t* out_size,
+                    char* err, size_t err_cap, int threads)
+{
+    if (err && err_cap) err[0] = 0;
+    ThreadPool* pool = nullptr;
+    if (threads > 1) { pool = new ThreadPool(threads); pool->init(); }
+    int rc = 0;
+    {
+        ffv1_frame F(pool);
+        raw_frame R;
+        R.Flavor = container == 0 ? raw_frame::flavor::DPX : raw_frame::flavor::TIFF;
+        R.Flavor_Private = (uint64_t)flavor;
+        F.RawFrame = &R;
+        F.SetWidth(width);
+        F.SetHeight(height);
+        F.OutOfBand(extradata, extradata_size);
+        if (F.ErrorMessage()) {
+            if (err) snprintf(err, err_cap, "%s", F.ErrorMessage());
+            rc = 1;
+        } else {
+            bool bad = F.Process(pkt, pkt_size);
+            if (bad || F.ErrorMessage()) {
+                if (err) snprintf(err, err_cap, "%s", F.ErrorMessage() ? F.ErrorMessage() : "Process returned true");
+                rc = 1;
+            }
+            if (R.Planes().empty()) { rc = rc ? rc : 2; }
+            else {
+                const buffer& B = R.Plane(0)->Buffer();
+                if (out_size) *out_size = B.Size();
+                if (B.Size() > out_cap) rc = rc ? rc : 2;
+                else memcpy(out, B.Data(), B.Size());
+            }
+        }
+    }
+    if (pool) { pool->shutdown(); delete pool; }
+    return rc;
+}
+
+// the reference's default state-transition table (Source/Lib/CoDec/FFV1/FFV1_Frame.cpp:35-55)
+extern const state_transitions_struct default_state_transitions;
+void ref_default_state_transitions(uint8_t out[256]) { memcpy(out, default_state_transitions.States, 256); }
+
+// CRC-32 as the reference computes it (Source/Lib/Utils/CRC32/ZenCRC32.cpp:1097-1135)
+uint32_t ref_crc32(const uint8_t* data, size_t size) { return ZenCRC32(data, size); }
+
+}
