@@ -103,7 +103,7 @@ def ref_decoder():
 
 def ref_decode(record, packet, width, height, layout, threads=1):
     """Decode one packet with the reference decoder into the file payload layout. Returns bytes; raises on decoder error.
-    The reference rounds the plane buffer up to 32 bits (RawFrame.h:62-68); that tail must be zero and is trimmed."""
+    The reference rounds the plane buffer up to 32 bits (RawFrame.h:62-68); that (uninitialised) tail is trimmed."""
     container, flavor = (0, layout) if layout < 32 else (1, {32: 0, 33: 1, 34: 2}[layout])
     cap = width * height * 8 + 4096
     out = np.zeros(cap, np.uint8)
@@ -115,7 +115,7 @@ def ref_decode(record, packet, width, height, layout, threads=1):
         raise RuntimeError("reference decoder: rc=%d %s" % (rc, err.value.decode()))
     from rawcooked_b200 import synth as S
     n = S.frame_bytes(width, height, layout)
-    assert osz.value - n in range(0, 4) and not out[n:osz.value].any(), (osz.value, n)
+    assert osz.value - n in range(0, 4), (osz.value, n)
     return out[:n].tobytes()
 
 
