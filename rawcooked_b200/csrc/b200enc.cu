@@ -1,0 +1,289 @@
+// C ABI of the B200 FFV1 encoder (include/b200enc.h): handle management, device memory plan, band loop.
+#include "../../include/b200enc.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ffv1_host.h"
+#include "ffv1_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? B200_ERR_NO_DEVICE : B200_ERR_CUDA;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail_cuda(e_, #x); } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n, std::vector<void*>& owned) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n ? n : 16);
+    if (e == cudaSuccess) { owned.push_back(q); *p = static_cast<T*>(q); }
+    return e;
+}
+
+}  // namespace
+
+struct b200_ffv1_enc {
+    b200_ffv1_cfg cfg;
+    b200::Ffv1Stream st;
+    b200::EncArgs args;
+    int max_frames = 0;
+    std::vector<void*> owned;       // device allocations
+    uint8_t* d_in = nullptr;        // staging for the host entry point (allocated on first use)
+    size_t max_packet = 0;
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t stats[8] = {0};
+    int last_frames = 0;
+    std::vector<uint64_t> h_off, h_len;
+    uint32_t* h_flags = nullptr;    // pinned mirror of flags
+};
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+uint32_t b200_version(void) { return (0u << 16) | (1u << 8) | 0u; }
+
+int b200_ffv1_slice_grid(uint32_t width, uint32_t height, int32_t slices, int32_t* num_h, int32_t* num_v) {
+    int h = 0, v = 0;
+    // the grid search does not depend on the bit depth except through a size cap that only matters above 8K
+    int r = b200::slice_grid(width, height, slices, 16, &h, &v);
+    if (r) return fail(B200_ERR_INVALID, "no slice grid for this -slices value");
+    if (num_h) *num_h = h;
+    if (num_v) *num_v = v;
+    return 0;
+}
+
+size_t b200_ffv1_frame_bytes(uint32_t width, uint32_t height, int32_t layout) {
+    return b200::layout_row_bytes(width, layout) * height;
+}
+
+int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
+    if (!cfg || !out) return fail(B200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->coder != 1) return fail(B200_ERR_INVALID, "only -coder 1 (range coder) is implemented");
+    if (cfg->max_frames < 1) return fail(B200_ERR_INVALID, "max_frames must be >= 1");
+    int ndev = 0;
+    cudaError_t de = cudaGetDeviceCount(&ndev);
+    if (de != cudaSuccess || ndev == 0) return fail(B200_ERR_NO_DEVICE, "no CUDA device: the B200 encoder has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(B200_ERR_INVALID, "bad device ordinal");
+    CU(cudaSetDevice(cfg->device));
+
+    b200_ffv1_enc* E = new (std::nothrow) b200_ffv1_enc;
+    if (!E) return fail(B200_ERR_INVALID, "out of host memory");
+    E->cfg = *cfg;
+    const char* err = "";
+    int r = b200::build_stream(cfg->width, cfg->height, cfg->layout, cfg->slices, cfg->context, cfg->slicecrc, &E->st, &err);
+    if (r) { delete E; return fail(r, err); }
+    const b200::Ffv1Stream& S = E->st;
+    const int ns = (int)S.slices.size();
+    const int B = cfg->max_frames;
+    E->max_frames = B;
+
+    int wmax = 0, hmax = 0;
+    for (const auto& g : S.slices) { wmax = g.w > wmax ? g.w : wmax; hmax = g.h > hmax ? g.h : hmax; }
+    wmax = (wmax + 3) & ~3;
+
+    b200::EncArgs& A = E->args;
+    std::memset(&A, 0, sizeof A);
+    A.W = (int)S.width; A.H = (int)S.height; A.layout = S.layout; A.bits = S.bits; A.sbits = S.sbits; A.swap_bg = S.swap_bg;
+    A.nslices = ns; A.nctx = S.nctx; A.is5 = S.is5; A.ec = S.ec;
+    A.row_bytes = (uint32_t)S.row_bytes; A.frame_bytes = S.frame_bytes;
+    A.band_rows = 16;
+    if (const char* e = getenv("B200_BAND_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 4096) A.band_rows = v; }
+    if (A.band_rows > hmax) A.band_rows = hmax;
+    A.nbands = (hmax + A.band_rows - 1) / A.band_rows;
+    A.wmax = wmax; A.hmax = hmax;
+
+    // the model kernel keeps the whole context-state table of one plane-set in shared memory
+    int dev_smem = 0;
+    cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    size_t need = b200::model_smem_bytes(S.nctx, wmax, 2);
+    if (need > (size_t)dev_smem) {
+        delete E;
+        char buf[200];
+        snprintf(buf, sizeof buf, "slice too wide for the shared-memory context model (%zu B needed, %d available): use more slices", need, dev_smem);
+        return fail(B200_ERR_INVALID, buf);
+    }
+    cudaError_t ce = b200::configure_kernels(S.nctx, wmax);
+    if (ce != cudaSuccess) { delete E; return fail_cuda(ce, "configure_kernels"); }
+
+    const int maxbins = 2 * S.sbits + 1;                        // bins of the largest symbol: 2e+3 with e = sbits-1
+    A.capY = (size_t)A.band_rows * wmax * maxbins;
+    A.capC = A.capY * 2;
+    size_t samples = (size_t)wmax * hmax * 3;
+    A.slice_cap = ((samples * (2 * S.bits + 5) / 8 + 1024 + 15) & ~(size_t)15);   // ffmpeg's own worst-case bound per sample
+    E->max_packet = A.slice_cap * ns;
+    A.arena_cap = E->max_packet * B;
+
+    auto& own = E->owned;
+    std::vector<uint16_t> hb((size_t)ns * b200::kMaxHeaderBins, 0);
+    std::vector<int32_t> hc(ns, 0);
+    for (int i = 0; i < ns; i++) {
+        if (S.header_bins[i].size() > (size_t)b200::kMaxHeaderBins) { delete E; return fail(B200_ERR_INVALID, "slice header too long"); }
+        hc[i] = (int32_t)S.header_bins[i].size();
+        std::memcpy(&hb[(size_t)i * b200::kMaxHeaderBins], S.header_bins[i].data(), S.header_bins[i].size() * 2);
+    }
+    uint8_t trans[512];
+    std::memcpy(trans, S.zero_state, 256);
+    std::memcpy(trans + 256, S.one_state, 256);
+
+    b200::SliceGeom* d_geom; int16_t* d_qtab; uint8_t* d_trans; uint16_t* d_hb; int32_t* d_hc; uint32_t* d_crc;
+#define ALLOC(p, n) do { cudaError_t e_ = dalloc(&(p), (n), own); if (e_ != cudaSuccess) { int rc_ = fail_cuda(e_, "cudaMalloc " #p); b200_ffv1_close(E); return rc_; } } while (0)
+    ALLOC(d_geom, sizeof(b200::SliceGeom) * ns);
+    ALLOC(d_qtab, sizeof S.qtab);
+    ALLOC(d_trans, 512);
+    ALLOC(d_hb, hb.size() * 2);
+    ALLOC(d_hc, hc.size() * 4);
+    ALLOC(d_crc, 1024);
+    ALLOC(A.state_save, (size_t)B * ns * 2 * S.nctx * 32);
+    ALLOC(A.binsY, (size_t)B * ns * A.capY * 2);
+    ALLOC(A.binsC, (size_t)B * ns * A.capC * 2);
+    ALLOC(A.rowcnt, (size_t)B * ns * A.band_rows * 2 * 4);
+    ALLOC(A.cstate, (size_t)B * ns * sizeof(b200::CoderState));
+    ALLOC(A.scratch, (size_t)B * ns * A.slice_cap);
+    ALLOC(A.slice_size, (size_t)B * ns * 4);
+    ALLOC(A.slice_off, (size_t)B * ns * 8);
+    ALLOC(A.frame_off, (size_t)B * 8);
+    ALLOC(A.frame_len, (size_t)B * 8);
+    ALLOC(A.arena, A.arena_cap);
+    ALLOC(A.flags, 64);
+#undef ALLOC
+    cudaMemcpy(d_geom, S.slices.data(), sizeof(b200::SliceGeom) * ns, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_qtab, S.qtab, sizeof S.qtab, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_trans, trans, 512, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_hb, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_hc, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_crc, b200::crc32_mpeg_table(), 1024, cudaMemcpyHostToDevice);
+    A.geom = d_geom; A.qtab = d_qtab; A.trans = d_trans; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
+    cudaError_t e2 = cudaHostAlloc((void**)&E->h_flags, 64, cudaHostAllocDefault);
+    if (e2 != cudaSuccess) { int rc = fail_cuda(e2, "cudaHostAlloc"); b200_ffv1_close(E); return rc; }
+    for (auto& ev : E->ev) cudaEventCreate(&ev);
+    E->h_off.resize(B); E->h_len.resize(B);
+    e2 = cudaDeviceSynchronize();
+    if (e2 != cudaSuccess) { int rc = fail_cuda(e2, "init"); b200_ffv1_close(E); return rc; }
+    *out = E;
+    return 0;
+}
+
+void b200_ffv1_close(b200_ffv1_enc* E) {
+    if (!E) return;
+    cudaSetDevice(E->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : E->owned) cudaFree(p);
+    if (E->d_in) cudaFree(E->d_in);
+    if (E->h_flags) cudaFreeHost(E->h_flags);
+    for (auto& ev : E->ev) if (ev) cudaEventDestroy(ev);
+    delete E;
+}
+
+size_t b200_ffv1_config_record(const b200_ffv1_enc* E, uint8_t* out, size_t cap) {
+    if (!E) return 0;
+    size_t n = E->st.config_record.size();
+    if (out && cap) std::memcpy(out, E->st.config_record.data(), n < cap ? n : cap);
+    return n;
+}
+
+size_t b200_ffv1_max_packet_bytes(const b200_ffv1_enc* E) { return E ? E->max_packet : 0; }
+
+int b200_ffv1_set_timing(b200_ffv1_enc* E, int32_t enabled) {
+    if (!E) return fail(B200_ERR_INVALID, "null encoder");
+    E->timing = enabled != 0;
+    return 0;
+}
+
+int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, void* stream) {
+    if (!E || !d_frames) return fail(B200_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CU(cudaSetDevice(E->cfg.device));
+    b200::EncArgs A = E->args;
+    A.in = static_cast<const uint8_t*>(d_frames);
+    CU(cudaMemsetAsync(A.flags, 0, 64, s));
+    uint64_t launches = 0;
+    for (int band = 0; band < A.nbands; band++) {
+        CU(b200::launch_model(A, band, n_frames, s));
+        CU(b200::launch_code(A, band, n_frames, s));
+        launches += 2;
+    }
+    CU(b200::launch_pack(A, n_frames, s));
+    launches += 2;
+    E->last_frames = n_frames;
+    E->stats[0] = launches;
+    E->stats[2] = (uint64_t)n_frames * E->st.width * E->st.height * 3;
+    return 0;
+}
+
+static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* out_len, uint64_t* total) {
+    if (n_frames != E->last_frames) return fail(B200_ERR_INVALID, "n_frames differs from the last encode call");
+    const b200::EncArgs& A = E->args;
+    CU(cudaMemcpy(E->h_flags, A.flags, 64, cudaMemcpyDeviceToHost));
+    if (E->h_flags[0] & 1u) return fail(B200_ERR_OVERFLOW, "slice scratch overflow");
+    if (E->h_flags[0] & 2u) return fail(B200_ERR_OVERFLOW, "packet arena overflow");
+    CU(cudaMemcpy(E->h_off.data(), A.frame_off, (size_t)n_frames * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(E->h_len.data(), A.frame_len, (size_t)n_frames * 8, cudaMemcpyDeviceToHost));
+    uint64_t tot = 0;
+    for (int i = 0; i < n_frames; i++) {
+        if (out_off) out_off[i] = (size_t)E->h_off[i];
+        if (out_len) out_len[i] = (size_t)E->h_len[i];
+        tot += E->h_len[i];
+    }
+    E->stats[1] = (uint64_t)E->h_flags[2] | ((uint64_t)E->h_flags[3] << 32);
+    E->stats[3] = tot;
+    if (total) *total = tot;
+    return 0;
+}
+
+int b200_ffv1_packets_device(b200_ffv1_enc* E, const void** d_arena, size_t* out_off, size_t* out_len, int32_t n_frames) {
+    if (!E) return fail(B200_ERR_INVALID, "null encoder");
+    CU(cudaSetDevice(E->cfg.device));
+    int r = collect(E, n_frames, out_off, out_len, nullptr);
+    if (r) return r;
+    if (d_arena) *d_arena = E->args.arena;
+    return 0;
+}
+
+int b200_ffv1_fetch_packets(b200_ffv1_enc* E, uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len, int32_t n_frames) {
+    if (!E || !out) return fail(B200_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(E->cfg.device));
+    uint64_t total = 0;
+    int r = collect(E, n_frames, out_off, out_len, &total);
+    if (r) return r;
+    if (total > out_cap) return fail(B200_ERR_OVERFLOW, "output buffer too small");
+    CU(cudaMemcpy(out, E->args.arena, (size_t)total, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames,
+                          uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len) {
+    if (!E || !frames || !out) return fail(B200_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
+    CU(cudaSetDevice(E->cfg.device));
+    const size_t fb = E->st.frame_bytes;
+    if (!E->d_in) CU(cudaMalloc((void**)&E->d_in, fb * E->max_frames));
+    for (int i = 0; i < n_frames; i++) {
+        if (!frames[i]) return fail(B200_ERR_INVALID, "null frame pointer");
+        CU(cudaMemcpyAsync(E->d_in + (size_t)i * fb, frames[i], fb, cudaMemcpyHostToDevice, 0));
+    }
+    int r = b200_ffv1_encode_device(E, E->d_in, n_frames, nullptr);
+    if (r) return r;
+    CU(cudaStreamSynchronize(0));
+    return b200_ffv1_fetch_packets(E, out, out_cap, out_off, out_len, n_frames);
+}
+
+int b200_ffv1_stats(const b200_ffv1_enc* E, uint64_t stats[8]) {
+    if (!E || !stats) return fail(B200_ERR_INVALID, "null argument");
+    std::memcpy(stats, E->stats, sizeof E->stats);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Device-side interface of the B200 FFV1 encoder: argument blocks and launchers of the four kernels.
+//
+//   k_model  (K1+K2+K3)  one CTA per (frame, slice, plane-set): unpack + forward RCT, median prediction, context
+//                         quantisation, binarisation, and resolution of the adaptive probability state every bin sees.
+//                         Emits, in bitstream order, one 16-bit (state | bit << 8) record per range-coder bin.
+//   k_code   (K4)         one lane per (frame, slice): the strictly serial part — range/low update, renormalisation,
+//                         carry handling, byte output, running CRC-32, slice footer.
+//   k_scan / k_pack       slice sizes -> packet layout; compaction of the per-slice byte streams into packets.
+//
+// Frames are processed in horizontal bands of `band_rows` rows so that the bin records (the only large intermediate)
+// never exceed two band buffers regardless of how many frames are in flight.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "ffv1_host.h"
+
+namespace b200 {
+
+constexpr int kModelThreads = 512;     // 16 warps: one CTA per SM when the large context model (162 KB) is in smem
+constexpr int kMaxHeaderBins = 96;
+
+// persistent range-coder registers of one slice between bands
+struct CoderState {
+    uint32_t low, range;
+    int32_t pending;        // outstanding byte, -1 = none yet
+    uint32_t run;           // outstanding 0xFF count
+    uint32_t pos;           // bytes written to the slice scratch so far
+    uint32_t crc;           // running CRC-32 of those bytes
+    uint32_t offY, offC;    // (unused between bands; kept for 32-byte alignment)
+};
+
+struct EncArgs {
+    // stream description
+    int32_t W, H, layout, bits, sbits, swap_bg, nslices, nctx, is5, ec;
+    uint32_t row_bytes;
+    size_t frame_bytes;
+    int32_t band_rows, nbands, wmax, hmax;
+    const SliceGeom* geom;        // [nslices]
+    const int16_t* qtab;          // [5][256]
+    const uint8_t* trans;         // [0..255] zero_state, [256..511] one_state
+    const uint16_t* hdr_bins;     // [nslices][kMaxHeaderBins]
+    const int32_t* hdr_cnt;       // [nslices]
+    const uint32_t* crc_table;    // [256]
+    // per batch
+    const uint8_t* in;            // frames back to back, stride frame_bytes
+    uint8_t* state_save;          // [frames][nslices][2][nctx*32]
+    uint16_t* binsY;              // [frames][nslices][capY]
+    uint16_t* binsC;              // [frames][nslices][capC]
+    size_t capY, capC;            // elements per (frame, slice) region
+    uint32_t* rowcnt;             // [frames][nslices][band_rows][2]
+    CoderState* cstate;           // [frames][nslices]
+    uint8_t* scratch;             // [frames][nslices][slice_cap]
+    size_t slice_cap;
+    uint32_t* slice_size;         // [frames][nslices]  bytes incl. footer
+    uint64_t* slice_off;          // [frames][nslices]  offset in arena
+    uint64_t* frame_off;          // [frames] offset of packet in arena
+    uint64_t* frame_len;          // [frames]
+    uint8_t* arena;
+    size_t arena_cap;
+    uint32_t* flags;              // [0] overflow flag, [1] total bins lo, [2] total bins hi
+};
+
+size_t model_smem_bytes(int nctx, int wmax, int planes);
+cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s);
+cudaError_t launch_code(const EncArgs& a, int band, int nframes, cudaStream_t s);
+cudaError_t launch_pack(const EncArgs& a, int nframes, cudaStream_t s);
+cudaError_t configure_kernels(int nctx, int wmax);
+
+}  // namespace b200

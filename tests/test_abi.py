@@ -1,0 +1,71 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/b200enc.h declares, does the
+host-only work (slice grid, payload sizes) correctly, and FAILS LOUDLY without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import util
+from rawcooked_b200 import ffv1, synth as S
+
+ROOT = util.ROOT
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "b200enc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = ffv1.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(L, s), "libb200enc.so does not export %s" % s
+
+
+def test_version_and_error_string():
+    L = ffv1.load_library()
+    assert L.b200_version() >= (1 << 8)
+    assert isinstance(L.b200_last_error(), bytes)
+
+
+@pytest.mark.parametrize("w,h,n", [(2048, 1556, 4), (3840, 2160, 24), (7680, 4320, 64), (640, 480, 16), (3840, 2160, 576), (1920, 1080, 9)])
+def test_slice_grid_equals_oracle(w, h, n):
+    assert ffv1.slice_grid(w, h, n) == util.oracle_grid(w, h, n, 16)
+
+
+def test_slice_grid_rejects_invalid_counts():
+    for n in (5, 7, 11, 13):          # not in the set ffmpeg accepts (reference test/slices.sh:12)
+        with pytest.raises(ffv1.B200Error):
+            ffv1.slice_grid(1920, 1080, n)
+
+
+@pytest.mark.parametrize("layout", sorted(S.LAYOUT_BITS))
+def test_frame_bytes(layout):
+    for w, h in ((64, 48), (100, 50), (3840, 2160)):
+        assert ffv1.frame_bytes(w, h, layout) == S.frame_bytes(w, h, layout) == util.oracle().ffv1o_frame_bytes(w, h, layout)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ffv1.B200Error) as e:
+        ffv1.FFV1Encoder(64, 48, S.DPX_RGB_16_BE, slices=4)
+    assert e.value.code == -2          # B200_ERR_NO_DEVICE
+
+
+def test_product_does_not_touch_oracle():
+    # the product path (package + csrc + include) must not reference anything under oracle/
+    bad = []
+    for base in ("rawcooked_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    if re.search(r"oracle[/.]|ffv1o_|libffv1_oracle|libref_", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
