@@ -103,18 +103,19 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     if (A.band_rows > hmax) A.band_rows = hmax;
     A.nbands = (hmax + A.band_rows - 1) / A.band_rows;
     A.wmax = wmax; A.hmax = hmax;
+    A.sstride = S.sbits <= 9 ? 27 : 32;
 
     // the model kernel keeps the whole context-state table of one plane-set in shared memory
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    size_t need = b200::model_smem_bytes(S.nctx, wmax, 2);
+    size_t need = b200::model_smem_bytes(S.nctx, A.sstride, wmax, 2);
     if (need > (size_t)dev_smem) {
         delete E;
         char buf[200];
         snprintf(buf, sizeof buf, "slice too wide for the shared-memory context model (%zu B needed, %d available): use more slices", need, dev_smem);
         return fail(B200_ERR_INVALID, buf);
     }
-    cudaError_t ce = b200::configure_kernels(S.nctx, wmax);
+    cudaError_t ce = b200::configure_kernels(S.nctx, A.sstride, wmax);
     if (ce != cudaSuccess) { delete E; return fail_cuda(ce, "configure_kernels"); }
 
     const int maxbins = 2 * S.sbits + 1;                        // bins of the largest symbol: 2e+3 with e = sbits-1
@@ -145,7 +146,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(d_hb, hb.size() * 2);
     ALLOC(d_hc, hc.size() * 4);
     ALLOC(d_crc, 1024);
-    ALLOC(A.state_save, (size_t)B * ns * 2 * S.nctx * 32);
+    ALLOC(A.state_save, (size_t)B * ns * 2 * (((size_t)S.nctx * A.sstride + 15) & ~(size_t)15));
     ALLOC(A.binsY, (size_t)B * ns * A.capY * 2);
     ALLOC(A.binsC, (size_t)B * ns * A.capC * 2);
     ALLOC(A.rowcnt, (size_t)B * ns * A.band_rows * 2 * 4);

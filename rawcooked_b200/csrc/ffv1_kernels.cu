@@ -82,8 +82,8 @@ struct ModelSmem {
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-size_t model_smem_bytes(int nctx, int wmax, int planes) {
-    size_t n = align16((size_t)nctx * 32);
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes) {
+    size_t n = align16((size_t)nctx * sstride);
     n += align16((size_t)3 * planes * wmax * 4);
     n += align16((size_t)wmax * 4) * 2;
     n += align16((size_t)wmax * 2);
@@ -91,9 +91,9 @@ size_t model_smem_bytes(int nctx, int wmax, int planes) {
     return n;
 }
 
-__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int wmax, int planes) {
+__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes) {
     ModelSmem m;
-    m.states = base; base += align16((size_t)nctx * 32);
+    m.states = base; base += align16((size_t)nctx * sstride);
     m.ring = reinterpret_cast<int32_t*>(base); base += align16((size_t)3 * planes * wmax * 4);
     m.val = reinterpret_cast<int32_t*>(base); base += align16((size_t)wmax * 4);
     m.off = reinterpret_cast<uint32_t*>(base); base += align16((size_t)wmax * 4);
@@ -115,12 +115,15 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     const int w = g.w, wmax = A.wmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kModelThreads / 32;
-    ModelSmem S = carve(smem_raw, A.nctx, wmax, planes);
+    ModelSmem S = carve(smem_raw, A.nctx, A.sstride, wmax, planes);
 
     const size_t fs = (size_t)frame * A.nslices + slice;
-    uint8_t* save = A.state_save + (fs * 2 + ps) * (size_t)A.nctx * 32;
+    const int state_bytes = (int)align16((size_t)A.nctx * A.sstride);
+    uint8_t* save = A.state_save + (fs * 2 + ps) * (size_t)state_bytes;
+    // 8-bit streams never use slots 10, 20, 21, 30, 31 (e <= 8): 27 states per context so the large model fits in smem
+    const int slot = A.sstride == 32 ? lane : lane - (lane > 10) - 2 * (lane > 21);
     {   // context states: 128 at the start of every frame (intra-only), else carried from the previous band
-        const int n16 = (A.nctx * 32) >> 4;
+        const int n16 = state_bytes >> 4;
         uint4* d = reinterpret_cast<uint4*>(S.states);
         if (band == 0) {
             const uint4 v = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                         else { n = e > 9 ? e - 9 : 0; i0 = e - 1; step = -1; }
                     }
                     if (n) {
-                        uint8_t* sp = S.states + cx * 32 + lane;
+                        uint8_t* sp = S.states + cx * A.sstride + slot;
                         uint32_t st = *sp;
                         for (int k = 0; k < n; k++) {
                             const int i = i0 + k * step;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
         if (tid == 0) A.rowcnt[(fs * A.band_rows + (y - r0)) * 2 + ps] = row_bins;
     }
     if (r1 < g.h) {   // carry the states to the next band
-        const int n16 = (A.nctx * 32) >> 4;
+        const int n16 = state_bytes >> 4;
         const uint4* s = reinterpret_cast<const uint4*>(S.states);
         uint4* d = reinterpret_cast<uint4*>(save);
         for (int i = tid; i < n16; i += kModelThreads) d[i] = s[i];
@@ -415,14 +418,14 @@ __global__ void __launch_bounds__(256) k_pack(const __grid_constant__ EncArgs A)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-cudaError_t configure_kernels(int nctx, int wmax) {
-    size_t need = model_smem_bytes(nctx, wmax, 2);
+cudaError_t configure_kernels(int nctx, int sstride, int wmax) {
+    size_t need = model_smem_bytes(nctx, sstride, wmax, 2);
     return cudaFuncSetAttribute(k_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }
 
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s) {
     dim3 grid(a.nslices * 2, nframes);
-    size_t smem = model_smem_bytes(a.nctx, a.wmax, 2);
+    size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2);
     k_model<<<grid, kModelThreads, smem, s>>>(a, band);
     return cudaGetLastError();
 }

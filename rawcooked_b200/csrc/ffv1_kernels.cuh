@@ -35,6 +35,7 @@ struct CoderState {
 struct EncArgs {
     // stream description
     int32_t W, H, layout, bits, sbits, swap_bg, nslices, nctx, is5, ec;
+    int32_t sstride;              // state bytes per context in the model kernel: 32, or 27 for 8-bit streams
     uint32_t row_bytes;
     size_t frame_bytes;
     int32_t band_rows, nbands, wmax, hmax;
@@ -46,7 +47,7 @@ struct EncArgs {
     const uint32_t* crc_table;    // [256]
     // per batch
     const uint8_t* in;            // frames back to back, stride frame_bytes
-    uint8_t* state_save;          // [frames][nslices][2][nctx*32]
+    uint8_t* state_save;          // [frames][nslices][2][align16(nctx*sstride)]
     uint16_t* binsY;              // [frames][nslices][capY]
     uint16_t* binsC;              // [frames][nslices][capC]
     size_t capY, capC;            // elements per (frame, slice) region
@@ -63,10 +64,10 @@ struct EncArgs {
     uint32_t* flags;              // [0] overflow flag, [1] total bins lo, [2] total bins hi
 };
 
-size_t model_smem_bytes(int nctx, int wmax, int planes);
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes);
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s);
 cudaError_t launch_code(const EncArgs& a, int band, int nframes, cudaStream_t s);
 cudaError_t launch_pack(const EncArgs& a, int nframes, cudaStream_t s);
-cudaError_t configure_kernels(int nctx, int wmax);
+cudaError_t configure_kernels(int nctx, int sstride, int wmax);
 
 }  // namespace b200
