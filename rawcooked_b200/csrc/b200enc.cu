@@ -100,11 +100,13 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     A.row_bytes = (uint32_t)S.row_bytes; A.frame_bytes = S.frame_bytes;
     A.band_rows = 16;
     if (const char* e = getenv("B200_BAND_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 4096) A.band_rows = v; }
+    if (A.band_rows > 64) A.band_rows = 64;
     if (A.band_rows > hmax) A.band_rows = hmax;
     A.nbands = (hmax + A.band_rows - 1) / A.band_rows;
     A.wmax = wmax; A.hmax = hmax;
     A.sstride = S.sbits <= 9 ? 27 : 32;
 
+    if (wmax > 4 * b200::kModelThreads) { delete E; return fail(B200_ERR_INVALID, "slice wider than 2048 pixels: use more slices"); }
     // the model kernel keeps the whole context-state table of one plane-set in shared memory
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
@@ -119,7 +121,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     if (ce != cudaSuccess) { delete E; return fail_cuda(ce, "configure_kernels"); }
 
     const int maxbins = 2 * S.sbits + 1;                        // bins of the largest symbol: 2e+3 with e = sbits-1
-    A.capY = (size_t)A.band_rows * wmax * maxbins;
+    A.capY = ((size_t)A.band_rows * ((size_t)wmax * maxbins + 64) + b200::kMaxHeaderBins + 63) & ~(size_t)63;   // + block padding per plane-row
     A.capC = A.capY * 2;
     size_t samples = (size_t)wmax * hmax * 3;
     A.slice_cap = ((samples * (2 * S.bits + 5) / 8 + 1024 + 15) & ~(size_t)15);   // ffmpeg's own worst-case bound per sample
@@ -132,7 +134,11 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     for (int i = 0; i < ns; i++) {
         if (S.header_bins[i].size() > (size_t)b200::kMaxHeaderBins) { delete E; return fail(B200_ERR_INVALID, "slice header too long"); }
         hc[i] = (int32_t)S.header_bins[i].size();
-        std::memcpy(&hb[(size_t)i * b200::kMaxHeaderBins], S.header_bins[i].data(), S.header_bins[i].size() * 2);
+        for (size_t k = 0; k < S.header_bins[i].size(); k++) {      // (state | bit << 8) -> coder record sp | bit << 9
+            const uint16_t r = S.header_bins[i][k];
+            const uint32_t st = r & 255u, bit = r >> 8;
+            hb[(size_t)i * b200::kMaxHeaderBins + k] = (uint16_t)((bit ? st : 256u - st) | (bit << 9));
+        }
     }
     uint8_t trans[512];
     std::memcpy(trans, S.zero_state, 256);
@@ -149,7 +155,10 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(A.state_save, (size_t)B * ns * 2 * (((size_t)S.nctx * A.sstride + 15) & ~(size_t)15));
     ALLOC(A.binsY, (size_t)B * ns * A.capY * 2);
     ALLOC(A.binsC, (size_t)B * ns * A.capC * 2);
-    ALLOC(A.rowcnt, (size_t)B * ns * A.band_rows * 2 * 4);
+    ALLOC(A.rowcnt, (size_t)B * ns * A.band_rows * 3 * 4);
+    ALLOC(A.ckptY, (size_t)B * ns * (A.capY >> 6) * 8);
+    ALLOC(A.ckptC, (size_t)B * ns * (A.capC >> 6) * 8);
+    ALLOC(A.used, (size_t)B * ns * 2 * 4);
     ALLOC(A.cstate, (size_t)B * ns * sizeof(b200::CoderState));
     ALLOC(A.scratch, (size_t)B * ns * A.slice_cap);
     ALLOC(A.slice_size, (size_t)B * ns * 4);
@@ -210,11 +219,12 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
     b200::EncArgs A = E->args;
     A.in = static_cast<const uint8_t*>(d_frames);
     CU(cudaMemsetAsync(A.flags, 0, 64, s));
+    CU(cudaMemsetAsync(A.scratch, 0, (size_t)n_frames * A.nslices * A.slice_cap, s));   // k_emit accumulates into it
     uint64_t launches = 0;
     for (int band = 0; band < A.nbands; band++) {
         CU(b200::launch_model(A, band, n_frames, s));
         CU(b200::launch_code(A, band, n_frames, s));
-        launches += 2;
+        launches += 3;
     }
     CU(b200::launch_pack(A, n_frames, s));
     launches += 2;

@@ -65,6 +65,8 @@ __device__ __forceinline__ void load_rgb(const uint8_t* __restrict__ row, int la
     }
 }
 
+constexpr uint32_t kNopRec = 0x100u;
+
 __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -104,6 +106,12 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     return m;
 }
 
+// bin record handed from k_model to k_code: sp | bit << 9 where sp = bit ? state : 256 - state is the 8-bit probability
+// of the coded value. kNopRec (sp = 256, bit 0) leaves the coder untouched and pads every plane-row to whole 16-byte chunks.
+__device__ __forceinline__ uint32_t make_rec(uint32_t st, uint32_t bit) { return (bit ? st : 256u - st) | (bit << 9); }
+
+constexpr int kMaxPixPerThread = 4;      // wmax <= 4 * kModelThreads
+
 __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int slice = blockIdx.x >> 1, ps = blockIdx.x & 1, frame = blockIdx.y;
@@ -138,35 +146,62 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
 
-    // RCT one payload row into ring slot (y+3)%3; rows above the slice are zero (FFV1_Slice.cpp:409-410 memset)
+    // forward RCT of pixel x of slice row y (inverse of Transform.cpp:29-37); p0 = Y or Cb, p1 = Cr
+    auto fetch = [&](int y, int x, int& p0, int& p1) {
+        const uint8_t* row = fin + (size_t)(g.y0 + y) * A.row_bytes;
+        int r, gg, b;
+        load_rgb(row, A.layout, g.x0 + x, r, gg, b);
+        if (A.swap_bg) { int t = gg; gg = b; b = t; }
+        b -= gg; r -= gg; gg += (b + r) >> 2; b += off; r += off;
+        if (ps == 0) { p0 = gg; p1 = 0; } else { p0 = b; p1 = r; }
+    };
+    // rows above the slice are zero (FFV1_Slice.cpp:409-410 memset)
     auto load_row = [&](int y) {
         int32_t* dst = S.ring + (size_t)((y + 3) % 3) * planes * wmax;
         if (y < 0) {
             for (int i = tid; i < planes * wmax; i += kModelThreads) dst[i] = 0;
             return;
         }
-        const uint8_t* row = fin + (size_t)(g.y0 + y) * A.row_bytes;
         for (int x = tid; x < w; x += kModelThreads) {
-            int r, gg, b;
-            load_rgb(row, A.layout, g.x0 + x, r, gg, b);
-            if (A.swap_bg) { int t = gg; gg = b; b = t; }
-            b -= gg; r -= gg; gg += (b + r) >> 2; b += off; r += off;
-            if (ps == 0) dst[x] = gg;
-            else { dst[x] = b; dst[wmax + x] = r; }
+            int p0, p1;
+            fetch(y, x, p0, p1);
+            dst[x] = p0;
+            if (ps) dst[wmax + x] = p1;
         }
     };
     load_row(r0 - 2);
     load_row(r0 - 1);
+    load_row(r0);
+    __syncthreads();
 
     uint16_t* bins = (ps ? A.binsC : A.binsY) + fs * (ps ? A.capC : A.capY);
-    uint32_t pos = 0;                       // bins emitted so far in this band (CTA-uniform)
+    uint32_t pos = 0;                       // records emitted so far in this band (CTA-uniform; segments start on multiples of 64)
+    uint32_t seg_extra = 0;                 // records already in the current segment (slice header ahead of the first Y row)
+    if (band == 0 && ps == 0) {
+        const int nh = A.hdr_cnt[slice];
+        for (int i = tid; i < nh; i += kModelThreads) bins[i] = A.hdr_bins[(size_t)slice * kMaxHeaderBins + i];
+        pos = seg_extra = (uint32_t)nh;
+    }
     const int K = (w + kModelThreads - 1) / kModelThreads;
     const int sbits = A.sbits;
+    // lane -> slot class of the symbol binarisation (rangecoder::s, FFV1_RangeCoder.cpp:135-171):
+    //   lane 0 zero flag | 1..10 exponent i = lane-1 (slot 10 also takes i > 9) | 11..21 sign for e = lane-11 |
+    //   22..31 mantissa bit i = lane-22 (slot 31 also takes i > 9)
+    const bool isB = lane >= 1 && lane <= 10, isD = lane >= 11 && lane <= 21;
+    const int li = isB ? lane - 1 : isD ? lane - 11 : lane - 22;
+    unsigned long long bins_total = 0;
 
     for (int y = r0; y < r1; y++) {
-        load_row(y);
-        __syncthreads();
-        uint32_t row_bins = 0;
+        // software prefetch of the next payload row into registers; it lands in the ring after this row is coded
+        int nx0[kMaxPixPerThread], nx1[kMaxPixPerThread];
+        const bool have_next = y + 1 < r1;
+        if (have_next) {
+#pragma unroll
+            for (int k = 0; k < kMaxPixPerThread; k++) {
+                const int x = tid + k * kModelThreads;
+                if (x < w) fetch(y + 1, x, nx0[k], nx1[k]);
+            }
+        }
         for (int pl = 0; pl < planes; pl++) {
             const int32_t* cur = S.ring + ((size_t)((y + 3) % 3) * planes + pl) * wmax;
             const int32_t* prv = S.ring + ((size_t)((y + 2) % 3) * planes + pl) * wmax;
@@ -213,6 +248,9 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
             // ---- K3: adaptive state seen by every bin. Warp `warp` owns the contexts with (ctx mod NW) == warp and walks
             // its samples in bitstream order; lane s owns slot s of the 32-state context (slots are independent chains).
             uint16_t* out = bins + pos;
+            const uint32_t seg_len = seg_extra + total;
+            const uint32_t pad = ((seg_len + 63u) & ~63u) - seg_len;
+            if (tid < (int)pad) out[total + tid] = (uint16_t)kNopRec;
             for (int c0 = 0; c0 < w; c0 += 32) {
                 const int xm = c0 + lane;
                 const uint32_t myctx = xm < w ? S.ctx[xm] : 0xFFFFu;
@@ -221,43 +259,65 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                     const int j = __ffs(todo) - 1;
                     todo &= todo - 1;
                     const uint32_t cx = __shfl_sync(0xffffffffu, myctx, j);
-                    const int v = S.val[c0 + j];
-                    const uint32_t ob = S.off[c0 + j];
-                    // which bins of this symbol live in slot `lane` (rangecoder::s, FFV1_RangeCoder.cpp:135-171)
+                    const int v = S.val[c0 + j];                 // warp-uniform
+                    uint16_t* o16 = out + S.off[c0 + j];
                     const uint32_t a = (uint32_t)abs(v);
                     const int e = 31 - __clz(a | 1);
-                    int n = 0, i0 = 0, step = 0;     // n bins; bin k uses index i = i0 + k*step
-                    if (lane == 0) n = 1;
-                    else if (v != 0) {
-                        if (lane <= 9) { n = (lane - 1) <= e; i0 = lane - 1; }
-                        else if (lane == 10) { n = e >= 9 ? e - 8 : 0; i0 = 9; step = 1; }
-                        else if (lane <= 21) { n = (lane - 11) == min(e, 10); }
-                        else if (lane <= 30) { n = (lane - 22) < e; i0 = lane - 22; }
-                        else { n = e > 9 ? e - 9 : 0; i0 = e - 1; step = -1; }
-                    }
-                    if (n) {
-                        uint8_t* sp = S.states + cx * A.sstride + slot;
-                        uint32_t st = *sp;
-                        for (int k = 0; k < n; k++) {
-                            const int i = i0 + k * step;
-                            uint32_t bit, idx;
-                            if (lane == 0) { bit = v == 0; idx = 0; }
-                            else if (lane <= 10) { bit = i < e; idx = 1 + i; }
-                            else if (lane <= 21) { bit = v < 0; idx = 2 * e + 2; }
-                            else { bit = (a >> i) & 1; idx = 2 * e + 1 - i; }
-                            out[ob + idx] = (uint16_t)(st | (bit << 8));
-                            st = S.trans[(bit << 8) | st];
+                    uint8_t* sp = S.states + cx * A.sstride + slot;
+                    if (e <= 8) {
+                        // every slot holds at most one bin of this symbol: branch-free selection per lane
+                        const bool nz = v != 0;
+                        const bool has = lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e));
+                        const uint32_t bit = lane == 0 ? !nz : isB ? (uint32_t)(li < e) : isD ? (uint32_t)(v < 0) : ((a >> li) & 1u);
+                        const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * e + 2 : 2 * e + 1 - li;
+                        if (has) {
+                            const uint32_t st = *sp;
+                            o16[idx] = (uint16_t)make_rec(st, bit);
+                            *sp = S.trans[(bit << 8) | st];
                         }
-                        *sp = (uint8_t)st;
+                    } else {
+                        // large symbols (e >= 9): slots 10 and 31 take several bins
+                        int n = 0, i0 = 0, step = 0;     // n bins; bin k uses index i = i0 + k*step
+                        if (lane == 0) n = 1;
+                        else if (lane <= 9) { n = 1; i0 = lane - 1; }
+                        else if (lane == 10) { n = e - 8; i0 = 9; step = 1; }
+                        else if (lane <= 21) { n = (lane - 11) == min(e, 10); }
+                        else if (lane <= 30) { n = 1; i0 = lane - 22; }
+                        else { n = e - 9; i0 = e - 1; step = -1; }
+                        if (n) {
+                            uint32_t st = *sp;
+                            for (int k = 0; k < n; k++) {
+                                const int i = i0 + k * step;
+                                uint32_t bit, idx;
+                                if (lane == 0) { bit = 0; idx = 0; }
+                                else if (lane <= 10) { bit = i < e; idx = 1 + i; }
+                                else if (lane <= 21) { bit = v < 0; idx = 2 * e + 2; }
+                                else { bit = (a >> i) & 1; idx = 2 * e + 1 - i; }
+                                o16[idx] = (uint16_t)make_rec(st, bit);
+                                st = S.trans[(bit << 8) | st];
+                            }
+                            *sp = (uint8_t)st;
+                        }
                     }
                 }
             }
-            pos += total;
-            row_bins += total;
+            if (tid == 0) A.rowcnt[(fs * A.band_rows + (y - r0)) * 3 + (ps ? 1 + pl : 0)] = seg_len;
+            pos += total + pad;
+            seg_extra = 0;
+            bins_total += total;
             __syncthreads();
         }
-        if (tid == 0) A.rowcnt[(fs * A.band_rows + (y - r0)) * 2 + ps] = row_bins;
+        if (have_next) {
+            int32_t* dst = S.ring + (size_t)((y + 4) % 3) * planes * wmax;
+#pragma unroll
+            for (int k = 0; k < kMaxPixPerThread; k++) {
+                const int x = tid + k * kModelThreads;
+                if (x < w) { dst[x] = nx0[k]; if (ps) dst[wmax + x] = nx1[k]; }
+            }
+            __syncthreads();
+        }
     }
+    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(A.flags + 2), bins_total);
     if (r1 < g.h) {   // carry the states to the next band
         const int n16 = state_bytes >> 4;
         const uint4* s = reinterpret_cast<const uint4*>(S.states);
@@ -267,107 +327,236 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_code: one lane per (frame, slice)
-struct Coder {
-    uint32_t low, range;
-    int32_t pending;
-    uint32_t run, pos, crc;
-    uint8_t* out;
-    uint32_t cap;
-    const uint32_t* crct;
-    bool overflow;
+// The range coder, split in two.
+//
+// A binary range coder's output is one big number: every bin with value 1 adds (range - range1) at the byte position the
+// coder has reached (FFV1_RangeCoder.cpp:71-102 seen from the encoder side: low += range - range1; on renormalisation the
+// top byte of the 16-bit window leaves). Only `range` and the number of renormalisations form a serial recurrence.
+//
+//   k_range  one lane per (frame, slice): runs just that recurrence — range' = renorm((range * sp + c) >> 8) and the
+//            shift count — over the slice's records, ~9 instructions per bin, branch-free, records staged through
+//            shared memory with cp.async. Every 64 records (one 128-byte block) it leaves a checkpoint (range, bytes so far).
+//   k_emit   one thread per 64-record block, fully parallel: replays the block from its checkpoint with the complete
+//            coder step and adds the block's contribution into the slice's byte stream, held as big-endian 32-bit words,
+//            with atomic adds (neighbouring blocks overlap by the 16-bit window and by carries; addition commutes).
+//
+// Slice header bins are ordinary records at the head of the Y stream (written by k_model), the terminator bin only moves
+// `range` (k_range), and the coder's final flush is a single +0xFF (k_range). CRC and footer: k_pack.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-    __device__ __forceinline__ void put(uint32_t b) {
-        if (pos < cap) out[pos] = (uint8_t)b; else overflow = true;
-        pos++;
-        crc = (crc << 8) ^ crct[(crc >> 24) ^ (b & 255u)];
+// add v into big-endian word idx of the slice stream, propagating wrap-arounds towards the front
+__device__ __forceinline__ void stream_add(uint32_t* W, int64_t idx, uint32_t v) {
+    while (v && idx >= 0) {
+        const uint32_t old = atomicAdd(W + idx, v);
+        v = (old + v < old) ? 1u : 0u;
+        idx--;
     }
-    __device__ __forceinline__ void shift() {      // one renormalisation step (range < 0x100 on entry)
-        if (pending < 0) pending = (int32_t)(low >> 8);
-        else if (low <= 0xFF00u) { put((uint32_t)pending); for (; run; run--) put(0xFFu); pending = (int32_t)(low >> 8); }
-        else if (low >= 0x10000u) { put((uint32_t)pending + 1); for (; run; run--) put(0u); pending = (int32_t)((low >> 8) & 255u); }
-        else run++;
-        low = (low & 255u) << 8;
-        range <<= 8;
-    }
-    __device__ __forceinline__ void bin(uint32_t rec) {
-        const uint32_t st = rec & 255u;
-        const uint32_t r1 = (range * st) >> 8;
-        if (rec & 256u) { low += range - r1; range = r1; }
-        else range -= r1;
-        if (range < 0x100u) shift();
-    }
-};
+}
 
-__global__ void __launch_bounds__(32) k_code(const __grid_constant__ EncArgs A, int band, int nframes) {
-    __shared__ uint32_t s_crc[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = A.crc_table[i];
-    __syncthreads();
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nframes * A.nslices) return;
-    const int slice = gid % A.nslices;
+__device__ __forceinline__ void range_step(uint32_t rec, uint32_t& range, uint32_t& cnt) {
+    const uint32_t sp = rec & 0x1FFu;
+    const uint32_t x = range * sp + ((rec & 0x200u) ? 0u : 255u);   // bit 0: range - ((range*state)>>8) == (range*(256-state)+255)>>8
+    const bool sh = x < 0x10000u;
+    range = sh ? (x & 0xFFFF00u) : (x >> 8);
+    cnt += sh;
+}
+
+constexpr int kRingBlocks = 4;          // 128-byte blocks in flight per lane
+constexpr int kMaxBandRows = 64;
+
+__global__ void __launch_bounds__(32) k_range(const __grid_constant__ EncArgs A, int band, int nframes) {
+    __shared__ uint4 s_ring[kRingBlocks][8][32];
+    __shared__ uint16_t s_cnt[kMaxBandRows * 3][32];                // blocks per segment (plane-row)
+    const int lane = threadIdx.x;
+    const int gid = blockIdx.x * 32 + lane;
+    const bool in_range = gid < nframes * A.nslices;
+    const int slice = in_range ? gid % A.nslices : 0;
     const SliceGeom g = A.geom[slice];
     const int r0 = band * A.band_rows;
-    if (r0 >= g.h) return;
+    const bool valid = in_range && r0 < g.h;
     const int r1 = min(r0 + A.band_rows, g.h);
+    const int nseg = valid ? (r1 - r0) * 3 : 0;
+    const size_t gsafe = in_range ? (size_t)gid : 0;
 
-    Coder c;
-    c.out = A.scratch + (size_t)gid * A.slice_cap;
-    c.cap = (uint32_t)A.slice_cap - 8;
-    c.crct = s_crc;
-    c.overflow = false;
-    if (band == 0) {
-        c.low = 0; c.range = 0xFF00u; c.pending = -1; c.run = 0; c.pos = 0; c.crc = 0;
-        const uint16_t* hb = A.hdr_bins + (size_t)slice * kMaxHeaderBins;
-        const int nh = A.hdr_cnt[slice];
-        for (int i = 0; i < nh; i++) c.bin(hb[i]);
-    } else {
-        const CoderState s = A.cstate[gid];
-        c.low = s.low; c.range = s.range; c.pending = s.pending; c.run = s.run; c.pos = s.pos; c.crc = s.crc;
-    }
-    const uint16_t* by = A.binsY + (size_t)gid * A.capY;
-    const uint16_t* bc = A.binsC + (size_t)gid * A.capC;
-    const uint32_t* rc = A.rowcnt + (size_t)gid * A.band_rows * 2;
-    uint64_t nb = 0;
-    for (int y = r0; y < r1; y++) {
-        const uint32_t ny = rc[(y - r0) * 2], nc = rc[(y - r0) * 2 + 1];
-        for (uint32_t i = 0; i < ny; i++) c.bin(by[i]);
-        by += ny;
-        for (uint32_t i = 0; i < nc; i++) c.bin(bc[i]);
-        bc += nc;
-        nb += ny + nc;
-    }
-    atomicAdd(reinterpret_cast<unsigned long long*>(A.flags + 2), (unsigned long long)nb);
-    if (r1 == g.h) {
-        c.bin(129u);                                           // terminator bin, state 129, bit 0 (FFV1_Slice.cpp:334-343)
-        c.range = 0xFFu; c.low += 0xFFu; c.shift();            // flush so that BytesUsed() == payload size (:297-299)
-        c.range = 0xFFu; c.shift();
-        const uint32_t n = c.pos;
-        c.cap += 8;
-        c.put(n >> 16); c.put(n >> 8); c.put(n);               // slice_size
-        if (A.ec) {
-            c.put(0);                                          // error_status
-            const uint32_t crc = c.crc;                        // parity: CRC of the whole slice becomes 0
-            c.put(crc >> 24); c.put(crc >> 16); c.put(crc >> 8); c.put(crc);
+    uint32_t total = 0, usedY = 0, usedC = 0;                       // 64-record blocks this lane consumes in this band
+    if (valid) {
+        const uint32_t* rc = A.rowcnt + gsafe * A.band_rows * 3;
+        for (int s = 0; s < nseg; s++) {
+            const uint32_t c = (rc[s] + 63u) >> 6;
+            s_cnt[s][lane] = (uint16_t)c;
+            total += c;
+            if (s % 3 == 0) usedY += c; else usedC += c;
         }
-        A.slice_size[gid] = c.pos;
-    } else {
-        CoderState s;
-        s.low = c.low; s.range = c.range; s.pending = c.pending; s.run = c.run; s.pos = c.pos; s.crc = c.crc; s.offY = 0; s.offC = 0;
-        A.cstate[gid] = s;
     }
-    if (c.overflow) atomicOr(A.flags, 1u);
+    if (in_range) { A.used[gsafe * 2] = usedY; A.used[gsafe * 2 + 1] = usedC; }
+    uint32_t maxb = total;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, o));
+
+    uint32_t range = 0xFF00u, cnt = 0;
+    if (valid && band > 0) { const CoderState s = A.cstate[gid]; range = s.range; cnt = s.pos; }
+
+    const uint4* pY = reinterpret_cast<const uint4*>(A.binsY + gsafe * A.capY);
+    const uint4* pC = reinterpret_cast<const uint4*>(A.binsC + gsafe * A.capC);
+    uint2* kY = A.ckptY + gsafe * (A.capY >> 6);
+    uint2* kC = A.ckptC + gsafe * (A.capC >> 6);
+    // two cursors over the lane's segments (Y row, Cb row, Cr row, Y row, ...): prefetch runs kRingBlocks-1 blocks ahead
+    int pf_seg = -1, pf_pl = 2, cs_seg = -1, cs_pl = 2;
+    uint32_t pf_rem = 0, cs_rem = 0;
+    auto next_src = [&]() -> const uint4* {
+        while (pf_rem == 0) {
+            if (++pf_seg >= nseg) return nullptr;
+            pf_pl = pf_pl == 2 ? 0 : pf_pl + 1;
+            pf_rem = s_cnt[pf_seg][lane];
+        }
+        pf_rem--;
+        const uint4* p = pf_pl == 0 ? pY : pC;
+        if (pf_pl == 0) pY += 8; else pC += 8;
+        return p;
+    };
+    auto next_ckpt = [&]() -> uint2* {
+        while (cs_rem == 0) {
+            if (++cs_seg >= nseg) return nullptr;
+            cs_pl = cs_pl == 2 ? 0 : cs_pl + 1;
+            cs_rem = s_cnt[cs_seg][lane];
+        }
+        cs_rem--;
+        return cs_pl == 0 ? kY++ : kC++;
+    };
+    auto prefetch = [&](int slot) {
+        const uint4* p = next_src();
+        if (p) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) cp_async16(&s_ring[slot][u][lane], p + u);
+        }
+        cp_async_commit();
+    };
+    for (int i = 0; i < kRingBlocks - 1; i++) prefetch(i);
+    const uint32_t nop2 = kNopRec | (kNopRec << 16);
+    for (uint32_t bi = 0; bi < maxb; bi++) {
+        prefetch((bi + kRingBlocks - 1) % kRingBlocks);
+        cp_async_wait<kRingBlocks - 1>();
+        const bool live = bi < total;
+        uint2* ck = next_ckpt();
+        if (ck) *ck = make_uint2(range, cnt);
+        const int slot = bi % kRingBlocks;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            uint4 q = s_ring[slot][u][lane];
+            if (!live) q = make_uint4(nop2, nop2, nop2, nop2);
+            range_step(q.x & 0xFFFFu, range, cnt); range_step(q.x >> 16, range, cnt);
+            range_step(q.y & 0xFFFFu, range, cnt); range_step(q.y >> 16, range, cnt);
+            range_step(q.z & 0xFFFFu, range, cnt); range_step(q.z >> 16, range, cnt);
+            range_step(q.w & 0xFFFFu, range, cnt); range_step(q.w >> 16, range, cnt);
+        }
+    }
+    cp_async_wait<0>();
+    if (valid) {
+        if (r1 == g.h) {
+            range_step(127u, range, cnt);                          // terminator: state 129, bit 0 (FFV1_Slice.cpp:334-343)
+            // final flush of the coder (so that the decoder's BytesUsed() lands on the end, FFV1_Slice.cpp:297-299):
+            // low += 0xFF in the current 16-bit window (stream bytes cnt, cnt+1), then two forced renormalisations
+            uint32_t* W = reinterpret_cast<uint32_t*>(A.scratch + gsafe * A.slice_cap);
+            const uint32_t q = cnt + 1;
+            if ((size_t)q + 8 < A.slice_cap) stream_add(W, q >> 2, 0xFFu << ((3 - (q & 3)) * 8));
+            else atomicOr(A.flags, 1u);
+            A.slice_size[gid] = cnt + 1;                           // cnt + 2 bytes produced; the last stays inside the coder
+        } else {
+            CoderState s;
+            s.low = 0; s.range = range; s.pending = 0; s.run = 0; s.pos = cnt; s.crc = 0; s.offY = 0; s.offC = 0;
+            A.cstate[gid] = s;
+        }
+    }
+}
+
+// k_emit: grid (blocks of 256 coder-blocks, stream Y/C, frame*slice)
+constexpr int kEmitThreads = 256;
+constexpr int kEmitWords = 22;          // local window: word 0 spare, then stream words (c0>>2)-1 ... (c0>>2)+19
+
+__global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ EncArgs A) {
+    __shared__ uint32_t s_loc[kEmitWords][kEmitThreads];
+    const int gid = blockIdx.z, stream = blockIdx.y, tid = threadIdx.x;
+    const uint32_t used = A.used[(size_t)gid * 2 + stream];
+    if (blockIdx.x * kEmitThreads >= used) return;
+    const uint32_t blk = blockIdx.x * kEmitThreads + tid;
+    if (blk >= used) return;
+    const size_t cap = stream ? A.capC : A.capY;
+    const uint4* src = reinterpret_cast<const uint4*>((stream ? A.binsC : A.binsY) + (size_t)gid * cap) + (size_t)blk * 8;
+    const uint2 ck = (stream ? A.ckptC : A.ckptY)[(size_t)gid * (cap >> 6) + blk];
+    uint4 q[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) q[u] = __ldg(src + u);
+#pragma unroll
+    for (int i = 0; i < kEmitWords; i++) s_loc[i][tid] = 0;
+
+    uint32_t range = ck.x;
+    const uint32_t c0 = ck.y;
+    // byte `lb` of the local window is stream byte 4*((c0>>2)-1) + lb - 4; the block starts at local byte 8 + (c0&3)
+    uint32_t lpos = 8 + (c0 & 3);           // local byte index of the coder window's high byte
+    uint64_t acc = 0;                       // bits 0..15 window, then pending bytes, then carry
+    uint32_t nsh = 0;
+    auto flush = [&](uint32_t extra) {
+        // the value above the window (pending bytes + carry) has its LSB at the end of local byte lpos + nsh/8 - 1;
+        // `extra` = 16 also retires the window itself (end of block)
+        const uint32_t k = nsh >> 3;
+        const uint64_t V = extra ? acc : (acc >> 16);
+        const uint32_t lb = lpos + k - 1 + (extra >> 3);
+        const uint32_t wi = lb >> 2, sft = (3 - (lb & 3)) * 8;
+        const uint64_t add = V << sft;
+        uint64_t cur = ((uint64_t)s_loc[wi - 1][tid] << 32) | s_loc[wi][tid];
+        const uint64_t sum = cur + add;
+        s_loc[wi - 1][tid] = (uint32_t)(sum >> 32);
+        s_loc[wi][tid] = (uint32_t)sum;
+        if (sum < cur) { int j = (int)wi - 2; while (j >= 0 && ++s_loc[j][tid] == 0) j--; }
+        lpos += k;
+        acc &= 0xFFFFull;
+        nsh = 0;
+    };
+    auto step = [&](uint32_t rec) {
+        const uint32_t sp = rec & 0x1FFu;
+        const uint32_t bit = (rec >> 9) & 1u;
+        const uint32_t x = range * sp + (bit ? 0u : 255u);
+        const uint32_t nr = x >> 8;
+        acc += bit ? (uint64_t)(range - nr) : 0ull;
+        const uint32_t sh = x < 0x10000u ? 8u : 0u;
+        range = nr << sh;
+        acc <<= sh;
+        nsh += sh;
+    };
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        step(q[u].x & 0xFFFFu); step(q[u].x >> 16); step(q[u].y & 0xFFFFu); step(q[u].y >> 16);
+        flush(0);
+        step(q[u].z & 0xFFFFu); step(q[u].z >> 16); step(q[u].w & 0xFFFFu); step(q[u].w >> 16);
+        flush(0);
+    }
+    flush(16);
+    uint32_t* W = reinterpret_cast<uint32_t*>(A.scratch + (size_t)gid * A.slice_cap);
+    const int64_t w0 = (int64_t)(c0 >> 2) - 2;                      // stream word of local word 0
+    if ((size_t)(c0 + 80) >= A.slice_cap) { atomicOr(A.flags, 1u); return; }
+#pragma unroll 1
+    for (int i = kEmitWords - 1; i >= 1; i--) {
+        const uint32_t v = s_loc[i][tid];
+        if (v) stream_add(W, w0 + i, v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_scan: slice sizes -> arena offsets (single CTA; the arrays are tiny)
+// k_scan: slice payload sizes -> slice sizes incl. footer -> arena offsets (single CTA; the arrays are tiny)
 __global__ void __launch_bounds__(1024) k_scan(const __grid_constant__ EncArgs A, int nframes) {
     __shared__ uint64_t s_part[1024];
     const int n = nframes * A.nslices;
+    const uint32_t foot = A.ec ? 8u : 3u;
     const int per = (n + 1023) / 1024;
     const int b = threadIdx.x * per, e = min(b + per, n);
     uint64_t sum = 0;
-    for (int i = b; i < e; i++) sum += A.slice_size[i];
+    for (int i = b; i < e; i++) sum += A.slice_size[i] + foot;
     s_part[threadIdx.x] = sum;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -379,42 +568,99 @@ __global__ void __launch_bounds__(1024) k_scan(const __grid_constant__ EncArgs A
     uint64_t off = s_part[threadIdx.x] - sum;
     for (int i = b; i < e; i++) {
         A.slice_off[i] = off;
-        off += A.slice_size[i];
+        off += A.slice_size[i] + foot;
     }
     __syncthreads();
     for (int f = threadIdx.x; f < nframes; f += 1024) {
         const int first = f * A.nslices, last = first + A.nslices - 1;
         A.frame_off[f] = A.slice_off[first];
-        A.frame_len[f] = A.slice_off[last] + A.slice_size[last] - A.slice_off[first];
+        A.frame_len[f] = A.slice_off[last] + A.slice_size[last] + foot - A.slice_off[first];
     }
     if (threadIdx.x == 1023 && s_part[1023] > A.arena_cap) atomicOr(A.flags, 2u);
 }
 
-// k_pack: copy each slice from its scratch region to its place in the arena (16-byte stores, funnel-shifted loads)
-__global__ void __launch_bounds__(256) k_pack(const __grid_constant__ EncArgs A) {
-    const int gid = blockIdx.x;
+// k_pack: one CTA per slice. Copies the payload from the slice scratch (big-endian 32-bit words, see k_emit) to its place in the packet arena, computes the
+// slice CRC in parallel and appends the footer: slice_size (24 bit BE), error_status 0, crc parity (32 bit BE)
+// (FFV1_Slice.cpp:247-253, :301-315). CRC = poly 0x04C11DB7, MSB first, init 0, no final xor — linear, so the CRC of a
+// concatenation is crc(A) * x^(8|B|) + crc(B) in GF(2)[x]/P (ZenCRC32 semantics, ZenCRC32.cpp:1097-1135).
+constexpr int kPackThreads = 256;
+__device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+#pragma unroll 4
+    for (int i = 31; i >= 0; i--) {
+        r = (r << 1) ^ ((r >> 31) ? 0x04C11DB7u : 0u);
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+__global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ EncArgs A) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_red[kPackThreads / 32];
+    const int gid = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < 256; i += kPackThreads) s_tab[i] = A.crc_table[i];
     const uint32_t n = A.slice_size[gid];
     const uint64_t off = A.slice_off[gid];
-    if (off + n > A.arena_cap) return;
+    const uint32_t foot = A.ec ? 8u : 3u;
+    if (off + n + foot > A.arena_cap || n + foot > A.slice_cap) return;
     const uint8_t* src = A.scratch + (size_t)gid * A.slice_cap;
     uint8_t* dst = A.arena + off;
+    __syncthreads();
+    // ---- CRC of the payload: thread t owns bytes [t*L, min((t+1)*L, n)), L a multiple of 16
+    uint32_t crc = 0;
+    if (A.ec) {
+        const uint32_t L = (((n + kPackThreads - 1) / kPackThreads) + 15u) & ~15u;
+        const uint32_t b0 = min(n, tid * L), b1 = min(n, b0 + L);
+        uint32_t i = b0;
+        for (; i + 16 <= b1; i += 16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+            const uint32_t wd[4] = {bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w)};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++) crc = (crc << 8) ^ s_tab[(crc >> 24) ^ ((wd[k] >> (8 * bb)) & 255u)];
+            }
+        }
+        for (; i < b1; i++) crc = (crc << 8) ^ s_tab[(crc >> 24) ^ src[i ^ 3]];
+        // multiply by x^(8 * bytes that follow this thread's piece) with square-and-multiply on x^8
+        uint32_t after = n - b1;
+        uint32_t pw = 0x00000100u;                 // x^8
+        while (after) {
+            if (after & 1u) crc = gf_mulmod(crc, pw);
+            after >>= 1;
+            if (after) pw = gf_mulmod(pw, pw);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = crc;
+    }
+    // ---- copy (16-byte stores, funnel-shifted loads: src is 16-byte aligned, dst is not)
     const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
-    const int t = blockIdx.y * blockDim.x + threadIdx.x, nt = gridDim.y * blockDim.x;
-    if (t < (int)head) dst[t] = src[t];
+    if (tid < (int)head) dst[tid] = src[tid ^ 3];
     const uint32_t body = (n - head) >> 4;
     const uint32_t sh = (head & 3) * 8;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + (head & ~3u));
     uint4* dv = reinterpret_cast<uint4*>(dst + head);
-    for (uint32_t i = t; i < body; i += nt) {
+    for (uint32_t i = tid; i < body; i += kPackThreads) {
         const uint32_t* p = sw + i * 4;
-        uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = sh ? p[4] : 0;
+        uint32_t w0 = bswap32(p[0]), w1 = bswap32(p[1]), w2 = bswap32(p[2]), w3 = bswap32(p[3]), w4 = sh ? bswap32(p[4]) : 0;
         uint4 v;
         v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
         v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
         dv[i] = v;
     }
     const uint32_t tail0 = head + (body << 4);
-    if (t < (int)(n - tail0)) dst[tail0 + t] = src[tail0 + t];
+    if (tid < (int)(n - tail0)) dst[tail0 + tid] = src[(tail0 + tid) ^ 3];
+    __syncthreads();
+    if (tid == 0) {
+        uint8_t f[8] = {(uint8_t)(n >> 16), (uint8_t)(n >> 8), (uint8_t)n, 0, 0, 0, 0, 0};
+        if (A.ec) {
+            uint32_t c = 0;
+            for (int i = 0; i < kPackThreads / 32; i++) c ^= s_red[i];
+            for (int i = 0; i < 4; i++) c = (c << 8) ^ s_tab[(c >> 24) ^ f[i]];
+            f[4] = (uint8_t)(c >> 24); f[5] = (uint8_t)(c >> 16); f[6] = (uint8_t)(c >> 8); f[7] = (uint8_t)c;
+        }
+        for (uint32_t i = 0; i < foot; i++) dst[n + i] = f[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -432,7 +678,11 @@ cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s
 
 cudaError_t launch_code(const EncArgs& a, int band, int nframes, cudaStream_t s) {
     int n = nframes * a.nslices;
-    k_code<<<(n + 31) / 32, 32, 0, s>>>(a, band, nframes);
+    k_range<<<(n + 31) / 32, 32, 0, s>>>(a, band, nframes);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const unsigned nblk = (unsigned)((a.capC >> 6) + kEmitThreads - 1) / kEmitThreads;
+    k_emit<<<dim3(nblk, 2, n), kEmitThreads, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -440,8 +690,7 @@ cudaError_t launch_pack(const EncArgs& a, int nframes, cudaStream_t s) {
     k_scan<<<1, 1024, 0, s>>>(a, nframes);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 grid(nframes * a.nslices, 4);
-    k_pack<<<grid, 256, 0, s>>>(a);
+    k_pack<<<nframes * a.nslices, kPackThreads, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -51,11 +51,14 @@ struct EncArgs {
     uint16_t* binsY;              // [frames][nslices][capY]
     uint16_t* binsC;              // [frames][nslices][capC]
     size_t capY, capC;            // elements per (frame, slice) region
-    uint32_t* rowcnt;             // [frames][nslices][band_rows][2]
+    uint32_t* rowcnt;             // [frames][nslices][band_rows][3]  bins of the Y, Cb, Cr row
+    uint2* ckptY;                 // [frames][nslices][capY/64]  (range, bytes so far) at the head of every 64-record block
+    uint2* ckptC;                 // [frames][nslices][capC/64]
+    uint32_t* used;               // [frames][nslices][2]  blocks in use in the Y / C stream of this band
     CoderState* cstate;           // [frames][nslices]
     uint8_t* scratch;             // [frames][nslices][slice_cap]
     size_t slice_cap;
-    uint32_t* slice_size;         // [frames][nslices]  bytes incl. footer
+    uint32_t* slice_size;         // [frames][nslices]  payload bytes (footer excluded)
     uint64_t* slice_off;          // [frames][nslices]  offset in arena
     uint64_t* frame_off;          // [frames] offset of packet in arena
     uint64_t* frame_len;          // [frames]

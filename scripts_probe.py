@@ -1,0 +1,18 @@
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np, torch
+from rawcooked_b200 import ffv1, synth as S
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+kind = sys.argv[2] if len(sys.argv) > 2 else "grain"
+w, h, layout = 3840, 2160, S.DPX_RGB_16_BE
+uniq = [S.synth_payload(w, h, layout, 3000 + k, kind) for k in range(2)]
+d = torch.stack([torch.from_numpy(uniq[k % 2]) for k in range(B)]).cuda()
+enc = ffv1.FFV1Encoder(w, h, layout, slices=24, max_frames=B)
+for it in range(3):
+    torch.cuda.synchronize(); t = time.perf_counter()
+    enc.encode_device(d.data_ptr(), B, 0)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t
+    print("B=%d %s: %.1f ms  %.1f fps  %.1f MPix/s" % (B, kind, dt * 1e3, B / dt, B * w * h / dt / 1e6))
+arena, off, ln = enc.packets_device(B)
+st = enc.stats()
+print(st, "bins/sample", st["bins"] / st["samples"], "ratio", st["packet_bytes"] / (B * enc.frame_bytes))
