@@ -35,7 +35,11 @@ cudaError_t dalloc(T** p, size_t n, std::vector<void*>& owned) {
 struct b200_ffv1_enc {
     b200_ffv1_cfg cfg;
     b200::Ffv1Stream st;
-    b200::EncArgs args;
+    b200::EncArgs args;             // band buffers of parity 0
+    b200::EncArgs args1;            // same, band buffers of parity 1 (double buffering across the three kernel streams)
+    cudaStream_t sm = nullptr, sr = nullptr, se = nullptr;   // model / range / emit streams
+    cudaEvent_t ev_start = nullptr, ev_model[2] = {nullptr, nullptr}, ev_range[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done_m = nullptr, ev_done_e = nullptr;
     int max_frames = 0;
     std::vector<void*> owned;       // device allocations
     uint8_t* d_in = nullptr;        // staging for the host entry point (allocated on first use)
@@ -153,12 +157,20 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(d_hc, hc.size() * 4);
     ALLOC(d_crc, 1024);
     ALLOC(A.state_save, (size_t)B * ns * 2 * (((size_t)S.nctx * A.sstride + 15) & ~(size_t)15));
+    b200::EncArgs& A1 = E->args1;
     ALLOC(A.binsY, (size_t)B * ns * A.capY * 2);
     ALLOC(A.binsC, (size_t)B * ns * A.capC * 2);
     ALLOC(A.rowcnt, (size_t)B * ns * A.band_rows * 3 * 4);
     ALLOC(A.ckptY, (size_t)B * ns * (A.capY >> 6) * 8);
     ALLOC(A.ckptC, (size_t)B * ns * (A.capC >> 6) * 8);
     ALLOC(A.used, (size_t)B * ns * 2 * 4);
+    uint16_t *bY1, *bC1; uint32_t *rc1, *us1; uint2 *kY1, *kC1;
+    ALLOC(bY1, (size_t)B * ns * A.capY * 2);
+    ALLOC(bC1, (size_t)B * ns * A.capC * 2);
+    ALLOC(rc1, (size_t)B * ns * A.band_rows * 3 * 4);
+    ALLOC(kY1, (size_t)B * ns * (A.capY >> 6) * 8);
+    ALLOC(kC1, (size_t)B * ns * (A.capC >> 6) * 8);
+    ALLOC(us1, (size_t)B * ns * 2 * 4);
     ALLOC(A.cstate, (size_t)B * ns * sizeof(b200::CoderState));
     ALLOC(A.scratch, (size_t)B * ns * A.slice_cap);
     ALLOC(A.slice_size, (size_t)B * ns * 4);
@@ -175,6 +187,14 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     cudaMemcpy(d_hc, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d_crc, b200::crc32_mpeg_table(), 1024, cudaMemcpyHostToDevice);
     A.geom = d_geom; A.qtab = d_qtab; A.trans = d_trans; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
+    A1 = A;
+    A1.binsY = bY1; A1.binsC = bC1; A1.rowcnt = rc1; A1.ckptY = kY1; A1.ckptC = kC1; A1.used = us1;
+    cudaStreamCreateWithFlags(&E->sm, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&E->sr, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&E->se, cudaStreamNonBlocking);
+    for (cudaEvent_t* ev : {&E->ev_start, &E->ev_model[0], &E->ev_model[1], &E->ev_range[0], &E->ev_range[1], &E->ev_emit[0],
+                            &E->ev_emit[1], &E->ev_done_m, &E->ev_done_e})
+        cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     cudaError_t e2 = cudaHostAlloc((void**)&E->h_flags, 64, cudaHostAllocDefault);
     if (e2 != cudaSuccess) { int rc = fail_cuda(e2, "cudaHostAlloc"); b200_ffv1_close(E); return rc; }
     for (auto& ev : E->ev) cudaEventCreate(&ev);
@@ -193,6 +213,10 @@ void b200_ffv1_close(b200_ffv1_enc* E) {
     if (E->d_in) cudaFree(E->d_in);
     if (E->h_flags) cudaFreeHost(E->h_flags);
     for (auto& ev : E->ev) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {E->ev_start, E->ev_model[0], E->ev_model[1], E->ev_range[0], E->ev_range[1], E->ev_emit[0], E->ev_emit[1],
+                           E->ev_done_m, E->ev_done_e})
+        if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {E->sm, E->sr, E->se}) if (st) cudaStreamDestroy(st);
     delete E;
 }
 
@@ -216,17 +240,40 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
     if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU(cudaSetDevice(E->cfg.device));
-    b200::EncArgs A = E->args;
-    A.in = static_cast<const uint8_t*>(d_frames);
-    CU(cudaMemsetAsync(A.flags, 0, 64, s));
-    CU(cudaMemsetAsync(A.scratch, 0, (size_t)n_frames * A.nslices * A.slice_cap, s));   // k_emit accumulates into it
+    b200::EncArgs A[2] = {E->args, E->args1};
+    A[0].in = A[1].in = static_cast<const uint8_t*>(d_frames);
+    CU(cudaMemsetAsync(A[0].flags, 0, 64, s));
+    CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)n_frames * A[0].nslices * A[0].slice_cap, s));   // k_emit accumulates into it
+    // Three kernels per band on three streams: model(b) -> range(b) -> emit(b); model(b) reuses the band buffers of
+    // parity b&1 once emit(b-2) has drained them. `s` (the caller's stream) forks into and joins from the three.
+    const bool serial = getenv("B200_SERIAL") != nullptr;     // debugging aid: everything on the caller's stream
+    cudaStream_t sm = serial ? s : E->sm, sr = serial ? s : E->sr, se = serial ? s : E->se;
     uint64_t launches = 0;
-    for (int band = 0; band < A.nbands; band++) {
-        CU(b200::launch_model(A, band, n_frames, s));
-        CU(b200::launch_code(A, band, n_frames, s));
+    if (!serial) {
+        CU(cudaEventRecord(E->ev_start, s));
+        CU(cudaStreamWaitEvent(sm, E->ev_start, 0));
+        CU(cudaStreamWaitEvent(sr, E->ev_start, 0));
+        CU(cudaStreamWaitEvent(se, E->ev_start, 0));
+    }
+    const int nb = A[0].nbands;
+    for (int band = 0; band < nb; band++) {
+        const int p = band & 1;
+        if (!serial && band >= 2) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
+        CU(b200::launch_model(A[p], band, n_frames, sm));
+        if (!serial) { CU(cudaEventRecord(E->ev_model[p], sm)); CU(cudaStreamWaitEvent(sr, E->ev_model[p], 0)); }
+        CU(b200::launch_range(A[p], band, n_frames, sr));
+        if (!serial) { CU(cudaEventRecord(E->ev_range[p], sr)); CU(cudaStreamWaitEvent(se, E->ev_range[p], 0)); }
+        CU(b200::launch_emit(A[p], n_frames, se));
+        if (!serial) CU(cudaEventRecord(E->ev_emit[p], se));
         launches += 3;
     }
-    CU(b200::launch_pack(A, n_frames, s));
+    if (!serial) {
+        CU(cudaEventRecord(E->ev_done_e, se));
+        CU(cudaStreamWaitEvent(s, E->ev_done_e, 0));
+        CU(cudaEventRecord(E->ev_done_m, sm));
+        CU(cudaStreamWaitEvent(s, E->ev_done_m, 0));
+    }
+    CU(b200::launch_pack(A[0], n_frames, s));
     launches += 2;
     E->last_frames = n_frames;
     E->stats[0] = launches;

@@ -676,11 +676,14 @@ cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_code(const EncArgs& a, int band, int nframes, cudaStream_t s) {
+cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s) {
     int n = nframes * a.nslices;
     k_range<<<(n + 31) / 32, 32, 0, s>>>(a, band, nframes);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit(const EncArgs& a, int nframes, cudaStream_t s) {
+    int n = nframes * a.nslices;
     const unsigned nblk = (unsigned)((a.capC >> 6) + kEmitThreads - 1) / kEmitThreads;
     k_emit<<<dim3(nblk, 2, n), kEmitThreads, 0, s>>>(a);
     return cudaGetLastError();

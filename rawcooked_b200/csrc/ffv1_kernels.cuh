@@ -69,7 +69,8 @@ struct EncArgs {
 
 size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes);
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s);
-cudaError_t launch_code(const EncArgs& a, int band, int nframes, cudaStream_t s);
+cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s);
+cudaError_t launch_emit(const EncArgs& a, int nframes, cudaStream_t s);
 cudaError_t launch_pack(const EncArgs& a, int nframes, cudaStream_t s);
 cudaError_t configure_kernels(int nctx, int sstride, int wmax);
 
