@@ -109,10 +109,16 @@ int b200_ffv1_packets_device(b200_ffv1_enc* enc, const void** d_arena, size_t* o
 int b200_ffv1_fetch_packets(b200_ffv1_enc* enc, uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len, int32_t n_frames);
 
 /* Counters of the last encode call: [0] kernels launched, [1] range-coder bins coded,
- * [2] samples coded, [3] bytes of packets produced; plus device time of the dominant kernels in
- * microseconds when timing is enabled via b200_ffv1_set_timing(): [4] model kernel, [5] coder kernel,
- * [6] pack kernel. Unused slots are 0. */
+ * [2] samples coded, [3] bytes of packets produced; plus, when timing is enabled with b200_ffv1_set_timing()
+ * (the kernels then run one after the other on the caller's stream, each bracketed by CUDA events), the summed
+ * device time in microseconds of [4] k_model, [5] k_range, [6] k_scan+k_pack, [7] k_emit over all bands.
+ * Valid after b200_ffv1_packets_device() / b200_ffv1_fetch_packets(). */
 int b200_ffv1_stats(const b200_ffv1_enc* enc, uint64_t stats[8]);
+
+/* Geometry of the encoder: [0] num_h_slices, [1] num_v_slices, [2] bands per frame (= launches of each band
+ * kernel per encode call), [3] rows per band, [4] slices per frame, [5] widest slice, [6] tallest slice,
+ * [7] bits_per_raw_sample. */
+int b200_ffv1_info(const b200_ffv1_enc* enc, int32_t info[8]);
 int b200_ffv1_set_timing(b200_ffv1_enc* enc, int32_t enabled);
 
 /* Text of the last error on this thread ("" if none). */

@@ -46,6 +46,8 @@ struct b200_ffv1_enc {
     size_t max_packet = 0;
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> tev;   // timing mode: 4 events per band + 2 around the pack kernels
+    bool timed_pending = false;
     uint64_t stats[8] = {0};
     int last_frames = 0;
     std::vector<uint64_t> h_off, h_len;
@@ -213,6 +215,7 @@ void b200_ffv1_close(b200_ffv1_enc* E) {
     if (E->d_in) cudaFree(E->d_in);
     if (E->h_flags) cudaFreeHost(E->h_flags);
     for (auto& ev : E->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : E->tev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : {E->ev_start, E->ev_model[0], E->ev_model[1], E->ev_range[0], E->ev_range[1], E->ev_emit[0], E->ev_emit[1],
                            E->ev_done_m, E->ev_done_e})
         if (ev) cudaEventDestroy(ev);
@@ -246,7 +249,14 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
     CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)n_frames * A[0].nslices * A[0].slice_cap, s));   // k_emit accumulates into it
     // Three kernels per band on three streams: model(b) -> range(b) -> emit(b); model(b) reuses the band buffers of
     // parity b&1 once emit(b-2) has drained them. `s` (the caller's stream) forks into and joins from the three.
-    const bool serial = getenv("B200_SERIAL") != nullptr;     // debugging aid: everything on the caller's stream
+    // timing mode (b200_ffv1_set_timing) and B200_SERIAL run everything on the caller's stream so that CUDA events can
+    // bracket each kernel
+    const bool serial = E->timing || getenv("B200_SERIAL") != nullptr;
+    if (E->timing && E->tev.empty()) {
+        E->tev.resize((size_t)A[0].nbands * 4 + 2);
+        for (auto& ev : E->tev) CU(cudaEventCreate(&ev));
+    }
+    const bool tm = E->timing;
     cudaStream_t sm = serial ? s : E->sm, sr = serial ? s : E->sr, se = serial ? s : E->se;
     uint64_t launches = 0;
     if (!serial) {
@@ -259,11 +269,15 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
     for (int band = 0; band < nb; band++) {
         const int p = band & 1;
         if (!serial && band >= 2) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
+        if (tm) CU(cudaEventRecord(E->tev[band * 4 + 0], s));
         CU(b200::launch_model(A[p], band, n_frames, sm));
+        if (tm) CU(cudaEventRecord(E->tev[band * 4 + 1], s));
         if (!serial) { CU(cudaEventRecord(E->ev_model[p], sm)); CU(cudaStreamWaitEvent(sr, E->ev_model[p], 0)); }
         CU(b200::launch_range(A[p], band, n_frames, sr));
+        if (tm) CU(cudaEventRecord(E->tev[band * 4 + 2], s));
         if (!serial) { CU(cudaEventRecord(E->ev_range[p], sr)); CU(cudaStreamWaitEvent(se, E->ev_range[p], 0)); }
         CU(b200::launch_emit(A[p], n_frames, se));
+        if (tm) CU(cudaEventRecord(E->tev[band * 4 + 3], s));
         if (!serial) CU(cudaEventRecord(E->ev_emit[p], se));
         launches += 3;
     }
@@ -273,7 +287,10 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
         CU(cudaEventRecord(E->ev_done_m, sm));
         CU(cudaStreamWaitEvent(s, E->ev_done_m, 0));
     }
+    if (tm) CU(cudaEventRecord(E->tev[(size_t)nb * 4], s));
     CU(b200::launch_pack(A[0], n_frames, s));
+    if (tm) CU(cudaEventRecord(E->tev[(size_t)nb * 4 + 1], s));
+    E->timed_pending = tm;
     launches += 2;
     E->last_frames = n_frames;
     E->stats[0] = launches;
@@ -296,6 +313,21 @@ static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* 
         tot += E->h_len[i];
     }
     E->stats[1] = (uint64_t)E->h_flags[2] | ((uint64_t)E->h_flags[3] << 32);
+    if (E->timed_pending) {      // device time of each kernel class in the last (serial, timed) encode, microseconds
+        double tmod = 0, trng = 0, temt = 0, tpk = 0;
+        float ms = 0;
+        const int nb = A.nbands;
+        CU(cudaEventSynchronize(E->tev[(size_t)nb * 4 + 1]));
+        for (int b = 0; b < nb; b++) {
+            cudaEventElapsedTime(&ms, E->tev[b * 4 + 0], E->tev[b * 4 + 1]); tmod += ms;
+            cudaEventElapsedTime(&ms, E->tev[b * 4 + 1], E->tev[b * 4 + 2]); trng += ms;
+            cudaEventElapsedTime(&ms, E->tev[b * 4 + 2], E->tev[b * 4 + 3]); temt += ms;
+        }
+        cudaEventElapsedTime(&ms, E->tev[(size_t)nb * 4], E->tev[(size_t)nb * 4 + 1]); tpk = ms;
+        E->stats[4] = (uint64_t)(tmod * 1000); E->stats[5] = (uint64_t)(trng * 1000); E->stats[6] = (uint64_t)(tpk * 1000);
+        E->stats[7] = (uint64_t)(temt * 1000);
+        E->timed_pending = false;
+    }
     E->stats[3] = tot;
     if (total) *total = tot;
     return 0;
@@ -336,6 +368,13 @@ int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_
     if (r) return r;
     CU(cudaStreamSynchronize(0));
     return b200_ffv1_fetch_packets(E, out, out_cap, out_off, out_len, n_frames);
+}
+
+int b200_ffv1_info(const b200_ffv1_enc* E, int32_t info[8]) {
+    if (!E || !info) return fail(B200_ERR_INVALID, "null argument");
+    info[0] = E->st.num_h; info[1] = E->st.num_v; info[2] = E->args.nbands; info[3] = E->args.band_rows;
+    info[4] = E->args.nslices; info[5] = E->args.wmax; info[6] = E->args.hmax; info[7] = E->st.bits;
+    return 0;
 }
 
 int b200_ffv1_stats(const b200_ffv1_enc* E, uint64_t stats[8]) {

@@ -51,6 +51,7 @@ def load_library():
     L.b200_ffv1_fetch_packets.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32]
     L.b200_ffv1_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.b200_ffv1_set_timing.argtypes = [C.c_void_p, C.c_int32]
+    L.b200_ffv1_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     _lib = L
     return L
 
@@ -86,6 +87,9 @@ class FFV1Encoder:
         self.width, self.height, self.layout, self.max_frames, self.device = width, height, layout, max_frames, device
         self.frame_bytes = frame_bytes(width, height, layout)
         self.grid = slice_grid(width, height, slices)
+        info = (C.c_int32 * 8)()
+        _check(self._L.b200_ffv1_info(self._h, info))
+        self.nbands, self.band_rows, self.nslices = info[2], info[3], info[4]
         n = self._L.b200_ffv1_config_record(self._h, None, 0)
         buf = C.create_string_buffer(n)
         self._L.b200_ffv1_config_record(self._h, buf, n)
@@ -143,7 +147,7 @@ class FFV1Encoder:
         s = (C.c_uint64 * 8)()
         _check(self._L.b200_ffv1_stats(self._h, s))
         return {"launches": s[0], "bins": s[1], "samples": s[2], "packet_bytes": s[3],
-                "model_us": s[4], "code_us": s[5], "pack_us": s[6]}
+                "model_us": s[4], "range_us": s[5], "pack_us": s[6], "emit_us": s[7]}
 
     def set_timing(self, enabled):
         _check(self._L.b200_ffv1_set_timing(self._h, 1 if enabled else 0))
