@@ -116,17 +116,22 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     // the model kernel keeps the whole context-state table of one plane-set in shared memory
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    size_t need = b200::model_smem_bytes(S.nctx, A.sstride, wmax, 2);
-    if (need > (size_t)dev_smem) {
+    const int maxbins = 2 * S.sbits + 1;                        // bins of the largest symbol: 2e+3 with e = sbits-1
+    size_t fixed = b200::model_smem_fixed(S.nctx, A.sstride, wmax, 2);
+    if (fixed + 4096 > (size_t)dev_smem) {
         delete E;
         char buf[200];
-        snprintf(buf, sizeof buf, "slice too wide for the shared-memory context model (%zu B needed, %d available): use more slices", need, dev_smem);
+        snprintf(buf, sizeof buf, "slice too wide for the shared-memory context model (%zu B needed, %d available): use more slices", fixed + 4096, dev_smem);
         return fail(B200_ERR_INVALID, buf);
     }
-    cudaError_t ce = b200::configure_kernels(S.nctx, A.sstride, wmax);
+    {   // whatever shared memory is left stages the records of a plane-row (rows that need more spill straight to global)
+        size_t room = ((size_t)dev_smem - fixed) / 2;
+        size_t want = (size_t)wmax * maxbins;
+        A.stage_cap = (int32_t)((room < want ? room : want) & ~(size_t)7);
+    }
+    cudaError_t ce = b200::configure_kernels(S.nctx, A.sstride, wmax, A.stage_cap);
     if (ce != cudaSuccess) { delete E; return fail_cuda(ce, "configure_kernels"); }
 
-    const int maxbins = 2 * S.sbits + 1;                        // bins of the largest symbol: 2e+3 with e = sbits-1
     A.capY = ((size_t)A.band_rows * ((size_t)wmax * maxbins + 64) + b200::kMaxHeaderBins + 63) & ~(size_t)63;   // + block padding per plane-row
     A.capC = A.capY * 2;
     size_t samples = (size_t)wmax * hmax * 3;

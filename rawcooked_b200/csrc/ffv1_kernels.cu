@@ -72,25 +72,46 @@ __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, 
 // ------------------------------------------------------------------------------------------------------------------
 // k_model
 //
-// shared memory carve-up (dynamic):
-//   states  nctx*32 B      adaptive state of every (context, slot) of this plane-set
+// One CTA per (frame, slice, plane-set) and band. Shared memory (dynamic):
+//   states  nctx*sstride B   adaptive state of every (context, slot) of this plane-set
 //   ring    3 rows x planes x wmax int32   RCT'd samples of rows y, y-1, y-2
-//   s_val   wmax int32     folded residual of the plane-row being coded (after the context-sign flip)
-//   s_off   wmax uint32    first bin of each sample inside the row
-//   s_ctx   wmax uint16    context index (>= 0)
-//   qtab 5*256 int16, trans 512 B, warp totals
+//   val/off/ctx per sample of the plane-row being coded: folded residual (after the context-sign flip), first record of the
+//           sample inside the row, context index (>= 0)
+//   cnt8    per-context occurrence counter inside the current plane-row (touched only by the warp owning the context)
+//   tmp8    per-sample scratch byte: position inside its chunk-class group, later the round of the sample
+//   plist   samples of the row partitioned by owner warp (ctx mod 16), each part in x order
+//   ccnt    [chunk][class] counts -> exclusive prefix over chunks; ctot/coff the same for record counts
+//   rlist   kRounds lists of samples: round r = samples whose context occurred r times earlier in the row
+//   stage   the row's records, copied out coalesced at the end of the row
+constexpr int kRounds = 8;
+constexpr int kMaxChunks = 64;            // wmax <= 2048
 struct ModelSmem {
-    uint8_t* states; int32_t* ring; int32_t* val; uint32_t* off; uint16_t* ctx; int16_t* qtab; uint8_t* trans; uint32_t* wtot;
+    uint8_t* states; int32_t* ring; int32_t* val; uint32_t* off; uint16_t* ctx; uint8_t* cnt8; uint8_t* tmp8; uint16_t* plist;
+    uint16_t* ccnt; uint32_t* ctot; uint16_t* clstot; uint16_t* cstart; uint16_t* rlist; uint32_t* rfill; uint32_t* misc;
+    uint16_t* stage; int16_t* qtab; uint8_t* trans;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-
-size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes) {
+__host__ __device__ inline int rlist_entries(int wmax) {  // NOLINT
+    int n = 0;
+    for (int r = 0; r < kRounds; r++) n += wmax / (r + 1) + 1;
+    return n;
+}
+// bytes of everything except the record staging area
+size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes) {
     size_t n = align16((size_t)nctx * sstride);
     n += align16((size_t)3 * planes * wmax * 4);
-    n += align16((size_t)wmax * 4) * 2;
-    n += align16((size_t)wmax * 2);
-    n += 5 * 256 * 2 + 512 + 32 * 4;
+    n += align16((size_t)wmax * 4) * 2;          // val, off
+    n += align16((size_t)wmax * 2) * 2;          // ctx, plist
+    n += align16((size_t)nctx);                  // cnt8
+    n += align16((size_t)wmax);                  // tmp8
+    n += kMaxChunks * 16 * 2 + kMaxChunks * 4 + 32 * 2 + 32 * 2;   // ccnt, ctot, clstot, cstart
+    n += align16((size_t)rlist_entries(wmax) * 2);
+    n += 16 * 4 + 16 * 4;                        // rfill, misc
+    n += 5 * 256 * 2 + 512;
     return n;
+}
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int stage_cap) {
+    return model_smem_fixed(nctx, sstride, wmax, planes) + align16((size_t)stage_cap * 2);
 }
 
 __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes) {
@@ -100,14 +121,25 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     m.val = reinterpret_cast<int32_t*>(base); base += align16((size_t)wmax * 4);
     m.off = reinterpret_cast<uint32_t*>(base); base += align16((size_t)wmax * 4);
     m.ctx = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
+    m.plist = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
+    m.cnt8 = base; base += align16((size_t)nctx);
+    m.tmp8 = base; base += align16((size_t)wmax);
+    m.ccnt = reinterpret_cast<uint16_t*>(base); base += kMaxChunks * 16 * 2;
+    m.ctot = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * 4;
+    m.clstot = reinterpret_cast<uint16_t*>(base); base += 32 * 2;
+    m.cstart = reinterpret_cast<uint16_t*>(base); base += 32 * 2;
+    m.rlist = reinterpret_cast<uint16_t*>(base); base += align16((size_t)rlist_entries(wmax) * 2);
+    m.rfill = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
+    m.misc = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
     m.qtab = reinterpret_cast<int16_t*>(base); base += 5 * 256 * 2;
     m.trans = base; base += 512;
-    m.wtot = reinterpret_cast<uint32_t*>(base);
+    m.stage = reinterpret_cast<uint16_t*>(base);
     return m;
 }
 
-// bin record handed from k_model to k_code: sp | bit << 9 where sp = bit ? state : 256 - state is the 8-bit probability
-// of the coded value. kNopRec (sp = 256, bit 0) leaves the coder untouched and pads every plane-row to whole 16-byte chunks.
+// bin record handed from k_model to k_range / k_emit: sp | bit << 9 where sp = bit ? state : 256 - state is the 8-bit
+// probability of the coded value. kNopRec (sp = 256, bit 0) leaves the coder untouched; it pads every plane-row to whole
+// 128-byte blocks.
 __device__ __forceinline__ uint32_t make_rec(uint32_t st, uint32_t bit) { return (bit ? st : 256u - st) | (bit << 9); }
 
 constexpr int kMaxPixPerThread = 4;      // wmax <= 4 * kModelThreads
@@ -122,14 +154,16 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     const int planes = ps ? 2 : 1;
     const int w = g.w, wmax = A.wmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
     constexpr int NW = kModelThreads / 32;
+    static_assert(NW == 16, "context classes are ctx & 15");
     ModelSmem S = carve(smem_raw, A.nctx, A.sstride, wmax, planes);
+    const uint32_t stage_cap = (uint32_t)A.stage_cap;
+    const bool compact = A.sstride != 32;   // 8-bit streams never use slots 10, 20, 21, 30, 31 (e <= 8): 27 states per context
 
     const size_t fs = (size_t)frame * A.nslices + slice;
     const int state_bytes = (int)align16((size_t)A.nctx * A.sstride);
     uint8_t* save = A.state_save + (fs * 2 + ps) * (size_t)state_bytes;
-    // 8-bit streams never use slots 10, 20, 21, 30, 31 (e <= 8): 27 states per context so the large model fits in smem
-    const int slot = A.sstride == 32 ? lane : lane - (lane > 10) - 2 * (lane > 21);
     {   // context states: 128 at the start of every frame (intra-only), else carried from the previous band
         const int n16 = state_bytes >> 4;
         uint4* d = reinterpret_cast<uint4*>(S.states);
@@ -142,6 +176,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
         }
         for (int i = tid; i < 5 * 256; i += kModelThreads) S.qtab[i] = A.qtab[i];
         for (int i = tid; i < 512; i += kModelThreads) S.trans[i] = A.trans[i];
+        for (int i = tid; i < (int)align16((size_t)A.nctx); i += kModelThreads) S.cnt8[i] = 0;
     }
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
@@ -172,7 +207,6 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     load_row(r0 - 2);
     load_row(r0 - 1);
     load_row(r0);
-    __syncthreads();
 
     uint16_t* bins = (ps ? A.binsC : A.binsY) + fs * (ps ? A.capC : A.capY);
     uint32_t pos = 0;                       // records emitted so far in this band (CTA-uniform; segments start on multiples of 64)
@@ -182,13 +216,22 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
         for (int i = tid; i < nh; i += kModelThreads) bins[i] = A.hdr_bins[(size_t)slice * kMaxHeaderBins + i];
         pos = seg_extra = (uint32_t)nh;
     }
-    const int K = (w + kModelThreads - 1) / kModelThreads;
+    __syncthreads();
+
+    const int nchunk = (w + 31) >> 5;
+    const int KC = (nchunk + NW - 1) / NW;  // 32-sample chunks per warp
     const int sbits = A.sbits;
-    // lane -> slot class of the symbol binarisation (rangecoder::s, FFV1_RangeCoder.cpp:135-171):
+    uint32_t* rl_off = S.misc + 4;           // first entry of round r in rlist
+    if (tid == 0) {
+        uint32_t o = 0;
+        for (int r = 0; r < kRounds; r++) { rl_off[r] = o; o += (uint32_t)(wmax / (r + 1) + 1); }
+    }
+    // lane -> slot class of the symbol binarisation for the slot-per-lane path (rangecoder::s, FFV1_RangeCoder.cpp:135-171):
     //   lane 0 zero flag | 1..10 exponent i = lane-1 (slot 10 also takes i > 9) | 11..21 sign for e = lane-11 |
     //   22..31 mantissa bit i = lane-22 (slot 31 also takes i > 9)
     const bool isB = lane >= 1 && lane <= 10, isD = lane >= 11 && lane <= 21;
     const int li = isB ? lane - 1 : isD ? lane - 11 : lane - 22;
+    const int lslot = compact ? lane - (lane > 10) - 2 * (lane > 21) : lane;
     unsigned long long bins_total = 0;
 
     for (int y = r0; y < r1; y++) {
@@ -206,105 +249,250 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
             const int32_t* cur = S.ring + ((size_t)((y + 3) % 3) * planes + pl) * wmax;
             const int32_t* prv = S.ring + ((size_t)((y + 2) % 3) * planes + pl) * wmax;
             const int32_t* pp2 = S.ring + ((size_t)((y + 1) % 3) * planes + pl) * wmax;
-            // ---- K2: prediction, context, fold; per-thread bin counts
-            uint32_t mine = 0;
-            const int xb = tid * K, xe = min(xb + K, w);
-            for (int x = xb; x < xe; x++) {
-                const int T = prv[x];
-                const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
-                const int L = x > 0 ? cur[x - 1] : prv[0];                 // sample[0][-1] = sample[1][0]
-                const int LT = x > 0 ? prv[x - 1] : pp2[0];                // what sample[1][-1] was set to one row earlier
-                int ctx = S.qtab[(L - LT) & 255] + S.qtab[256 + ((LT - T) & 255)] + S.qtab[512 + ((T - RT) & 255)];
-                if (A.is5) {
-                    const int LL = x > 1 ? cur[x - 2] : (x == 1 ? prv[0] : 0);
-                    const int TT = pp2[x];
-                    ctx += S.qtab[768 + ((LL - L) & 255)] + S.qtab[1024 + ((TT - T) & 255)];
-                }
-                int d = cur[x] - median3(L, L + T - LT, T);
-                if (ctx < 0) { ctx = -ctx; d = -d; }
-                d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
-                S.val[x] = d;
-                S.ctx[x] = (uint16_t)ctx;
-                mine += d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
-            }
-            // ---- exclusive scan of bin counts over the row
-            uint32_t incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (lane == 31) S.wtot[warp] = incl;
-            __syncthreads();
-            uint32_t wv = lane < NW ? S.wtot[lane] : 0, wincl = wv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o); if (lane >= o) wincl += t; }
-            const uint32_t total = __shfl_sync(0xffffffffu, wincl, NW - 1);
-            const uint32_t wbase = __shfl_sync(0xffffffffu, wincl - wv, warp);
-            uint32_t o = wbase + incl - mine;
-            for (int x = xb; x < xe; x++) {
-                S.off[x] = o;
-                const int d = S.val[x];
-                o += d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
-            }
-            __syncthreads();
-            // ---- K3: adaptive state seen by every bin. Warp `warp` owns the contexts with (ctx mod NW) == warp and walks
-            // its samples in bitstream order; lane s owns slot s of the 32-state context (slots are independent chains).
             uint16_t* out = bins + pos;
-            const uint32_t seg_len = seg_extra + total;
-            const uint32_t pad = ((seg_len + 63u) & ~63u) - seg_len;
-            if (tid < (int)pad) out[total + tid] = (uint16_t)kNopRec;
-            for (int c0 = 0; c0 < w; c0 += 32) {
-                const int xm = c0 + lane;
-                const uint32_t myctx = xm < w ? S.ctx[xm] : 0xFFFFu;
-                uint32_t todo = __ballot_sync(0xffffffffu, xm < w && (int)(myctx % NW) == warp);
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const uint32_t cx = __shfl_sync(0xffffffffu, myctx, j);
-                    const int v = S.val[c0 + j];                 // warp-uniform
-                    uint16_t* o16 = out + S.off[c0 + j];
-                    const uint32_t a = (uint32_t)abs(v);
-                    const int e = 31 - __clz(a | 1);
-                    uint8_t* sp = S.states + cx * A.sstride + slot;
-                    if (e <= 8) {
-                        // every slot holds at most one bin of this symbol: branch-free selection per lane
-                        const bool nz = v != 0;
-                        const bool has = lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e));
-                        const uint32_t bit = lane == 0 ? !nz : isB ? (uint32_t)(li < e) : isD ? (uint32_t)(v < 0) : ((a >> li) & 1u);
-                        const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * e + 2 : 2 * e + 1 - li;
-                        if (has) {
-                            const uint32_t st = *sp;
-                            o16[idx] = (uint16_t)make_rec(st, bit);
-                            *sp = S.trans[(bit << 8) | st];
-                        }
-                    } else {
-                        // large symbols (e >= 9): slots 10 and 31 take several bins
-                        int n = 0, i0 = 0, step = 0;     // n bins; bin k uses index i = i0 + k*step
-                        if (lane == 0) n = 1;
-                        else if (lane <= 9) { n = 1; i0 = lane - 1; }
-                        else if (lane == 10) { n = e - 8; i0 = 9; step = 1; }
-                        else if (lane <= 21) { n = (lane - 11) == min(e, 10); }
-                        else if (lane <= 30) { n = 1; i0 = lane - 22; }
-                        else { n = e - 9; i0 = e - 1; step = -1; }
-                        if (n) {
-                            uint32_t st = *sp;
-                            for (int k = 0; k < n; k++) {
-                                const int i = i0 + k * step;
-                                uint32_t bit, idx;
-                                if (lane == 0) { bit = 0; idx = 0; }
-                                else if (lane <= 10) { bit = i < e; idx = 1 + i; }
-                                else if (lane <= 21) { bit = v < 0; idx = 2 * e + 2; }
-                                else { bit = (a >> i) & 1; idx = 2 * e + 1 - i; }
-                                o16[idx] = (uint16_t)make_rec(st, bit);
-                                st = S.trans[(bit << 8) | st];
-                            }
-                            *sp = (uint8_t)st;
-                        }
+            if (tid <= kRounds) S.rfill[tid] = 0;
+            // ---- phase A (K2): prediction, context, fold, records per sample; per-chunk record totals and per-chunk counts of
+            // every context class (class = ctx & 15 = owner warp)
+            for (int k = 0; k < KC; k++) {
+                const int c = warp * KC + k;
+                const int x = c * 32 + lane;
+                const bool valid = x < w;
+                uint32_t nb = 0, cls = 16 + lane;
+                if (valid) {
+                    const int T = prv[x];
+                    const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
+                    const int L = x > 0 ? cur[x - 1] : prv[0];                 // sample[0][-1] = sample[1][0]
+                    const int LT = x > 0 ? prv[x - 1] : pp2[0];                // what sample[1][-1] was set to one row earlier
+                    int ctx = S.qtab[(L - LT) & 255] + S.qtab[256 + ((LT - T) & 255)] + S.qtab[512 + ((T - RT) & 255)];
+                    if (A.is5) {
+                        const int LL = x > 1 ? cur[x - 2] : (x == 1 ? prv[0] : 0);
+                        const int TT = pp2[x];
+                        ctx += S.qtab[768 + ((LL - L) & 255)] + S.qtab[1024 + ((TT - T) & 255)];
+                    }
+                    int d = cur[x] - median3(L, L + T - LT, T);
+                    if (ctx < 0) { ctx = -ctx; d = -d; }
+                    d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
+                    S.val[x] = d;
+                    S.ctx[x] = (uint16_t)ctx;
+                    nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
+                    cls = (uint32_t)ctx & 15u;
+                }
+                uint32_t incl = nb;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const uint32_t m = __match_any_sync(0xffffffffu, cls);
+                if (c < kMaxChunks) {
+                    if (lane < 16) S.ccnt[c * 16 + lane] = 0;
+                    if (lane == 31) S.ctot[c] = incl;
+                }
+                __syncwarp();
+                if (valid) {
+                    S.off[x] = incl - nb;                                      // chunk-relative for now
+                    const uint32_t intra = __popc(m & lt);
+                    S.tmp8[x] = (uint8_t)intra;
+                    if (intra == 0) S.ccnt[c * 16 + cls] = (uint16_t)__popc(m);
+                }
+            }
+            __syncthreads();
+            // ---- phase B1: exclusive prefix over chunks of the class counts (warp q: class q) and of the record totals (warp 0)
+            {
+                const int q = warp;
+                const int c0 = lane, c1 = lane + 32;
+                uint32_t v0 = c0 < nchunk ? S.ccnt[c0 * 16 + q] : 0u, v1 = c1 < nchunk ? S.ccnt[c1 * 16 + q] : 0u;
+                uint32_t i0 = v0, i1 = v1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) { i0 += t0; i1 += t1; }
+                }
+                const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+                if (c0 < nchunk) S.ccnt[c0 * 16 + q] = (uint16_t)(i0 - v0);
+                if (c1 < nchunk) S.ccnt[c1 * 16 + q] = (uint16_t)(tot0 + i1 - v1);
+                if (lane == 0) S.clstot[q] = (uint16_t)(tot0 + tot1);
+                if (warp == 0) {
+                    uint32_t a0 = c0 < nchunk ? S.ctot[c0] : 0u, a1 = c1 < nchunk ? S.ctot[c1] : 0u;
+                    uint32_t j0 = a0, j1 = a1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t t0 = __shfl_up_sync(0xffffffffu, j0, o), t1 = __shfl_up_sync(0xffffffffu, j1, o);
+                        if (lane >= o) { j0 += t0; j1 += t1; }
+                    }
+                    const uint32_t s0 = __shfl_sync(0xffffffffu, j0, 31), s1 = __shfl_sync(0xffffffffu, j1, 31);
+                    if (c0 < nchunk) S.ctot[c0] = j0 - a0;
+                    if (c1 < nchunk) S.ctot[c1] = s0 + j1 - a1;
+                    if (lane == 0) S.misc[0] = s0 + s1;                        // records of this plane-row
+                }
+            }
+            __syncthreads();
+            // ---- phase B2: final record offsets; samples partitioned by owner warp, x order kept
+            const uint32_t total = S.misc[0];
+            {
+                uint32_t ct = lane < 16 ? S.clstot[lane] : 0u, ci = ct;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ci, o); if (lane >= o) ci += t; }
+                const uint32_t cst = ci - ct;                                   // lane q < 16: first plist entry of class q
+                if (warp == 0 && lane < 16) S.cstart[lane] = (uint16_t)cst;
+                for (int k = 0; k < KC; k++) {
+                    const int c = warp * KC + k;
+                    const int x = c * 32 + lane;
+                    const bool valid = x < w;
+                    const uint32_t cls = valid ? (S.ctx[x] & 15u) : 0u;
+                    const uint32_t base = __shfl_sync(0xffffffffu, cst, cls);
+                    if (valid) {
+                        S.off[x] += S.ctot[c];
+                        S.plist[base + S.ccnt[c * 16 + cls] + S.tmp8[x]] = (uint16_t)x;
                     }
                 }
             }
-            if (tid == 0) A.rowcnt[(fs * A.band_rows + (y - r0)) * 3 + (ps ? 1 + pl : 0)] = seg_len;
-            pos += total + pad;
-            seg_extra = 0;
-            bins_total += total;
+            __syncthreads();
+            // ---- phase C: warp q ranks the samples of its context class: round = occurrences of the context earlier in the row
+            {
+                const uint32_t n = S.clstot[warp], base = S.cstart[warp];
+                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                    const bool valid = i0 + lane < n;
+                    const uint32_t x = valid ? S.plist[base + i0 + lane] : 0u;
+                    const uint32_t cx = valid ? S.ctx[x] : (0x10000u | lane);
+                    const uint32_t m = __match_any_sync(0xffffffffu, cx);
+                    const uint32_t b0 = valid ? S.cnt8[cx] : 0u;
+                    const uint32_t r = b0 + __popc(m & lt);
+                    __syncwarp();
+                    if (valid && (m >> lane) == 1u) S.cnt8[cx] = (uint8_t)min(255u, b0 + __popc(m));   // highest lane of the group
+                    __syncwarp();
+                    const uint32_t rr = valid ? min(r, (uint32_t)kRounds) : (32u + lane);
+                    const uint32_t m2 = __match_any_sync(0xffffffffu, rr);
+                    const int lead = __ffs(m2) - 1;
+                    uint32_t bs = 0;
+                    if (valid && lead == lane) bs = atomicAdd(&S.rfill[rr], (uint32_t)__popc(m2));
+                    bs = __shfl_sync(0xffffffffu, bs, lead);
+                    if (valid) {
+                        S.tmp8[x] = (uint8_t)rr;
+                        if (rr < (uint32_t)kRounds) S.rlist[rl_off[rr] + bs + __popc(m2 & lt)] = (uint16_t)x;
+                    }
+                }
+                __syncwarp();
+                for (uint32_t i0 = lane; i0 < n; i0 += 32) S.cnt8[S.ctx[S.plist[base + i0]]] = 0;
+            }
+            __syncthreads();
+            // ---- phase D (K3): one sample per lane, all its bins; round by round (contexts inside a round are distinct)
+            for (int r = 0; r < kRounds; r++) {
+                const uint32_t nr = S.rfill[r];
+                if (nr == 0) break;
+                for (uint32_t i0 = (uint32_t)warp * 32; i0 < nr; i0 += kModelThreads) {
+                    const bool act = i0 + lane < nr;
+                    uint32_t nb = 0, e = 0, o = 0, sgnslot = 0;
+                    uint64_t bw = 0;
+                    uint8_t* sb = S.states;
+                    if (act) {
+                        const uint32_t x = S.rlist[rl_off[r] + i0 + lane];
+                        const int v = S.val[x];
+                        o = S.off[x];
+                        sb = S.states + (uint32_t)S.ctx[x] * A.sstride;
+                        const uint32_t a = (uint32_t)abs(v);
+                        if (v == 0) { nb = 1; bw = 1; }
+                        else {
+                            e = 31 - __clz(a);
+                            nb = 2 * e + 3;
+                            const uint32_t mant = e ? (__brev(a & ((1u << e) - 1u)) >> (32 - e)) : 0u;   // bit i of a -> bit e-1-i
+                            bw = (uint64_t)(((1u << e) - 1u) << 1) | ((uint64_t)mant << (e + 2)) | ((uint64_t)(v < 0) << (2 * e + 2));
+                            sgnslot = 11 + min(e, 10u);
+                        }
+                    }
+                    const uint32_t nbmax = __reduce_max_sync(0xffffffffu, nb);
+                    for (uint32_t b = 0; b < nbmax; b++) {
+                        if (b < nb) {
+                            // bins 0..e+1: zero flag and unary exponent (slots 0, 1..10); then mantissa (22..31) from the top bit down,
+                            // last the sign (11..21)
+                            const uint32_t t = nb - 1 - b;
+                            uint32_t slot = b <= e + 1 ? min(b, 10u) : (t == 0 ? sgnslot : 21u + min(t, 10u));
+                            if (compact) slot = slot - (slot > 10) - 2 * (slot > 21);
+                            const uint32_t bit = (uint32_t)(bw >> b) & 1u;
+                            const uint32_t st = sb[slot];
+                            sb[slot] = S.trans[(bit << 8) | st];
+                            const uint32_t rec = make_rec(st, bit);
+                            const uint32_t idx = o + b;
+                            if (idx < stage_cap) S.stage[idx] = (uint16_t)rec; else out[idx] = (uint16_t)rec;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- phase E: samples beyond kRounds occurrences of their context (flat areas): the owner warp walks them in x order,
+            // one sample per step, lane s = slot s of the context (slots are independent chains)
+            if (S.rfill[kRounds]) {
+                const uint32_t n = S.clstot[warp], base = S.cstart[warp];
+                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                    const bool valid = i0 + lane < n;
+                    const uint32_t xl = valid ? S.plist[base + i0 + lane] : 0u;
+                    uint32_t todo = __ballot_sync(0xffffffffu, valid && S.tmp8[xl] == kRounds);
+                    while (todo) {
+                        const int j = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const uint32_t x = __shfl_sync(0xffffffffu, xl, j);
+                        const int v = S.val[x];                 // warp-uniform
+                        const uint32_t ob = S.off[x];
+                        const uint32_t a = (uint32_t)abs(v);
+                        const int e = 31 - __clz(a | 1);
+                        uint8_t* sp = S.states + (uint32_t)S.ctx[x] * A.sstride + lslot;
+                        if (e <= 8) {
+                            const bool nz = v != 0;
+                            const bool has = lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e));
+                            const uint32_t bit = lane == 0 ? !nz : isB ? (uint32_t)(li < e) : isD ? (uint32_t)(v < 0) : ((a >> li) & 1u);
+                            const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * e + 2 : 2 * e + 1 - li;
+                            if (has) {
+                                const uint32_t st = *sp;
+                                const uint32_t rec = make_rec(st, bit);
+                                if (ob + idx < stage_cap) S.stage[ob + idx] = (uint16_t)rec; else out[ob + idx] = (uint16_t)rec;
+                                *sp = S.trans[(bit << 8) | st];
+                            }
+                        } else {
+                            int n2 = 0, i0b = 0, step = 0;     // n2 bins; bin k uses index i = i0b + k*step
+                            if (lane == 0) n2 = 1;
+                            else if (lane <= 9) { n2 = 1; i0b = lane - 1; }
+                            else if (lane == 10) { n2 = e - 8; i0b = 9; step = 1; }
+                            else if (lane <= 21) { n2 = (lane - 11) == min(e, 10); }
+                            else if (lane <= 30) { n2 = 1; i0b = lane - 22; }
+                            else { n2 = e - 9; i0b = e - 1; step = -1; }
+                            if (n2) {
+                                uint32_t st = *sp;
+                                for (int k = 0; k < n2; k++) {
+                                    const int i = i0b + k * step;
+                                    uint32_t bit, idx;
+                                    if (lane == 0) { bit = 0; idx = 0; }
+                                    else if (lane <= 10) { bit = i < e; idx = 1 + i; }
+                                    else if (lane <= 21) { bit = v < 0; idx = 2 * e + 2; }
+                                    else { bit = (a >> i) & 1; idx = 2 * e + 1 - i; }
+                                    const uint32_t rec = make_rec(st, bit);
+                                    if (ob + idx < stage_cap) S.stage[ob + idx] = (uint16_t)rec; else out[ob + idx] = (uint16_t)rec;
+                                    st = S.trans[(bit << 8) | st];
+                                }
+                                *sp = (uint8_t)st;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- phase F: staged records -> global, coalesced; pad the segment to a whole 128-byte block with no-op records
+            {
+                const uint32_t ns = min(total, stage_cap);
+                if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+                    const uint32_t nv = ns >> 3;
+                    const uint4* sv = reinterpret_cast<const uint4*>(S.stage);
+                    uint4* dv = reinterpret_cast<uint4*>(out);
+                    for (uint32_t i = tid; i < nv; i += kModelThreads) dv[i] = sv[i];
+                    for (uint32_t i = (nv << 3) + tid; i < ns; i += kModelThreads) out[i] = S.stage[i];
+                } else {
+                    for (uint32_t i = tid; i < ns; i += kModelThreads) out[i] = S.stage[i];
+                }
+                const uint32_t seg_len = seg_extra + total;
+                const uint32_t pad = ((seg_len + 63u) & ~63u) - seg_len;
+                if (tid < (int)pad) out[total + tid] = (uint16_t)kNopRec;
+                if (tid == 0) A.rowcnt[(fs * A.band_rows + (y - r0)) * 3 + (ps ? 1 + pl : 0)] = seg_len;
+                pos += total + pad;
+                seg_extra = 0;
+                bins_total += total;
+            }
             __syncthreads();
         }
         if (have_next) {
@@ -664,14 +852,14 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ E
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-cudaError_t configure_kernels(int nctx, int sstride, int wmax) {
-    size_t need = model_smem_bytes(nctx, sstride, wmax, 2);
+cudaError_t configure_kernels(int nctx, int sstride, int wmax, int stage_cap) {
+    size_t need = model_smem_bytes(nctx, sstride, wmax, 2, stage_cap);
     return cudaFuncSetAttribute(k_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }
 
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s) {
     dim3 grid(a.nslices * 2, nframes);
-    size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2);
+    size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.stage_cap);
     k_model<<<grid, kModelThreads, smem, s>>>(a, band);
     return cudaGetLastError();
 }

@@ -39,6 +39,7 @@ struct EncArgs {
     uint32_t row_bytes;
     size_t frame_bytes;
     int32_t band_rows, nbands, wmax, hmax;
+    int32_t stage_cap;            // records of one plane-row k_model can stage in shared memory (the rest go straight to global)
     const SliceGeom* geom;        // [nslices]
     const int16_t* qtab;          // [5][256]
     const uint8_t* trans;         // [0..255] zero_state, [256..511] one_state
@@ -67,11 +68,12 @@ struct EncArgs {
     uint32_t* flags;              // [0] overflow flag, [1] total bins lo, [2] total bins hi
 };
 
-size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes);
+size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes);
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int stage_cap);
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s);
 cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s);
 cudaError_t launch_emit(const EncArgs& a, int nframes, cudaStream_t s);
 cudaError_t launch_pack(const EncArgs& a, int nframes, cudaStream_t s);
-cudaError_t configure_kernels(int nctx, int sstride, int wmax);
+cudaError_t configure_kernels(int nctx, int sstride, int wmax, int stage_cap);
 
 }  // namespace b200
