@@ -83,7 +83,7 @@ __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, 
 //   ccnt    [chunk][class] counts -> exclusive prefix over chunks; ctot/coff the same for record counts
 //   rlist   kRounds lists of samples: round r = samples whose context occurred r times earlier in the row
 //   stage   the row's records, copied out coalesced at the end of the row
-constexpr int kRounds = 8;
+constexpr int kRounds = 2;
 constexpr int kMaxChunks = 64;            // wmax <= 2048
 struct ModelSmem {
     uint8_t* states; int32_t* ring; int32_t* val; uint32_t* off; uint16_t* ctx; uint8_t* cnt8; uint8_t* tmp8; uint16_t* plist;
@@ -143,6 +143,13 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
 __device__ __forceinline__ uint32_t make_rec(uint32_t st, uint32_t bit) { return (bit ? st : 256u - st) | (bit << 9); }
 
 constexpr int kMaxPixPerThread = 4;      // wmax <= 4 * kModelThreads
+
+// Byte offset of (context, slot) in the shared-memory state table. With 32 states per context every row starts on the
+// same 8 banks as the row four contexts further, so the word inside the row is XOR-swizzled with context bits 2..4:
+// lanes that touch the same slot of different contexts then spread over all 32 banks.
+__device__ __forceinline__ uint32_t state_off(uint32_t ctx, uint32_t slot, bool compact) {
+    return compact ? ctx * 27u + slot : ctx * 32u + (slot ^ (((ctx >> 2) & 7u) << 2));
+}
 
 __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -381,12 +388,12 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                     const bool act = i0 + lane < nr;
                     uint32_t nb = 0, e = 0, o = 0, sgnslot = 0;
                     uint64_t bw = 0;
-                    uint8_t* sb = S.states;
+                    uint32_t cxd = 0;
                     if (act) {
                         const uint32_t x = S.rlist[rl_off[r] + i0 + lane];
                         const int v = S.val[x];
                         o = S.off[x];
-                        sb = S.states + (uint32_t)S.ctx[x] * A.sstride;
+                        cxd = S.ctx[x];
                         const uint32_t a = (uint32_t)abs(v);
                         if (v == 0) { nb = 1; bw = 1; }
                         else {
@@ -406,8 +413,9 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                             uint32_t slot = b <= e + 1 ? min(b, 10u) : (t == 0 ? sgnslot : 21u + min(t, 10u));
                             if (compact) slot = slot - (slot > 10) - 2 * (slot > 21);
                             const uint32_t bit = (uint32_t)(bw >> b) & 1u;
-                            const uint32_t st = sb[slot];
-                            sb[slot] = S.trans[(bit << 8) | st];
+                            uint8_t* sp = S.states + state_off(cxd, slot, compact);
+                            const uint32_t st = *sp;
+                            *sp = S.trans[(bit << 8) | st];
                             const uint32_t rec = make_rec(st, bit);
                             const uint32_t idx = o + b;
                             if (idx < stage_cap) S.stage[idx] = (uint16_t)rec; else out[idx] = (uint16_t)rec;
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                         const uint32_t ob = S.off[x];
                         const uint32_t a = (uint32_t)abs(v);
                         const int e = 31 - __clz(a | 1);
-                        uint8_t* sp = S.states + (uint32_t)S.ctx[x] * A.sstride + lslot;
+                        uint8_t* sp = S.states + state_off(S.ctx[x], (uint32_t)lslot, compact);
                         if (e <= 8) {
                             const bool nz = v != 0;
                             const bool has = lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e));
