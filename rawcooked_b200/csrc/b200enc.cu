@@ -185,7 +185,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(A.frame_off, (size_t)B * 8);
     ALLOC(A.frame_len, (size_t)B * 8);
     ALLOC(A.arena, A.arena_cap);
-    ALLOC(A.flags, 64);
+    ALLOC(A.flags, 256);
 #undef ALLOC
     cudaMemcpy(d_geom, S.slices.data(), sizeof(b200::SliceGeom) * ns, cudaMemcpyHostToDevice);
     cudaMemcpy(d_qtab, S.qtab, sizeof S.qtab, cudaMemcpyHostToDevice);
@@ -202,7 +202,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     for (cudaEvent_t* ev : {&E->ev_start, &E->ev_model[0], &E->ev_model[1], &E->ev_range[0], &E->ev_range[1], &E->ev_emit[0],
                             &E->ev_emit[1], &E->ev_done_m, &E->ev_done_e})
         cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
-    cudaError_t e2 = cudaHostAlloc((void**)&E->h_flags, 64, cudaHostAllocDefault);
+    cudaError_t e2 = cudaHostAlloc((void**)&E->h_flags, 256, cudaHostAllocDefault);
     if (e2 != cudaSuccess) { int rc = fail_cuda(e2, "cudaHostAlloc"); b200_ffv1_close(E); return rc; }
     for (auto& ev : E->ev) cudaEventCreate(&ev);
     E->h_off.resize(B); E->h_len.resize(B);
@@ -250,7 +250,7 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
     CU(cudaSetDevice(E->cfg.device));
     b200::EncArgs A[2] = {E->args, E->args1};
     A[0].in = A[1].in = static_cast<const uint8_t*>(d_frames);
-    CU(cudaMemsetAsync(A[0].flags, 0, 64, s));
+    CU(cudaMemsetAsync(A[0].flags, 0, 256, s));
     CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)n_frames * A[0].nslices * A[0].slice_cap, s));   // k_emit accumulates into it
     // Three kernels per band on three streams: model(b) -> range(b) -> emit(b); model(b) reuses the band buffers of
     // parity b&1 once emit(b-2) has drained them. `s` (the caller's stream) forks into and joins from the three.
@@ -306,7 +306,11 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
 static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* out_len, uint64_t* total) {
     if (n_frames != E->last_frames) return fail(B200_ERR_INVALID, "n_frames differs from the last encode call");
     const b200::EncArgs& A = E->args;
-    CU(cudaMemcpy(E->h_flags, A.flags, 64, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(E->h_flags, A.flags, 256, cudaMemcpyDeviceToHost));
+    if (getenv("B200_PHASE_TIMING")) {
+        const unsigned long long* ph = reinterpret_cast<const unsigned long long*>(E->h_flags + 16);
+        fprintf(stderr, "k_model phase cycles (sum over CTAs): A %llu B1 %llu B2 %llu C %llu D %llu E %llu F %llu next-row %llu\n", ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+    }
     if (E->h_flags[0] & 1u) return fail(B200_ERR_OVERFLOW, "slice scratch overflow");
     if (E->h_flags[0] & 2u) return fail(B200_ERR_OVERFLOW, "packet arena overflow");
     CU(cudaMemcpy(E->h_off.data(), A.frame_off, (size_t)n_frames * 8, cudaMemcpyDeviceToHost));

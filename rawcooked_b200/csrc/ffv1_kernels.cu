@@ -85,10 +85,12 @@ __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, 
 //   stage   the row's records, copied out coalesced at the end of the row
 constexpr int kRounds = 2;
 constexpr int kMaxChunks = 64;            // wmax <= 2048
+constexpr int kSlutRow = 36;              // slot of bin b of a symbol with exponent e: slut[e * kSlutRow + b], e <= 16, b <= 34
+constexpr int kSlutBytes = 17 * kSlutRow + 12;   // 624, keeps 16-byte alignment
 struct ModelSmem {
     uint8_t* states; int32_t* ring; int32_t* val; uint32_t* off; uint16_t* ctx; uint8_t* cnt8; uint8_t* tmp8; uint16_t* plist;
     uint16_t* ccnt; uint32_t* ctot; uint16_t* clstot; uint16_t* cstart; uint16_t* rlist; uint32_t* rfill; uint32_t* misc;
-    uint16_t* stage; int16_t* qtab; uint8_t* trans;
+    uint16_t* stage; int16_t* qtab; uint8_t* trans; uint8_t* slut; uint32_t* t2;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 __host__ __device__ inline int rlist_entries(int wmax) {  // NOLINT
@@ -107,7 +109,7 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes) {
     n += kMaxChunks * 16 * 2 + kMaxChunks * 4 + 32 * 2 + 32 * 2;   // ccnt, ctot, clstot, cstart
     n += align16((size_t)rlist_entries(wmax) * 2);
     n += 16 * 4 + 16 * 4;                        // rfill, misc
-    n += 5 * 256 * 2 + 512;
+    n += 5 * 256 * 2 + 512 + kSlutBytes + 512 * 4;
     return n;
 }
 size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int stage_cap) {
@@ -133,6 +135,8 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     m.misc = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
     m.qtab = reinterpret_cast<int16_t*>(base); base += 5 * 256 * 2;
     m.trans = base; base += 512;
+    m.slut = base; base += kSlutBytes;
+    m.t2 = reinterpret_cast<uint32_t*>(base); base += 512 * 4;
     m.stage = reinterpret_cast<uint16_t*>(base);
     return m;
 }
@@ -143,6 +147,13 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
 __device__ __forceinline__ uint32_t make_rec(uint32_t st, uint32_t bit) { return (bit ? st : 256u - st) | (bit << 9); }
 
 constexpr int kMaxPixPerThread = 4;      // wmax <= 4 * kModelThreads
+
+// -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
+#ifdef B200_PHASE_TIMING
+#define PHASE_MARK(k) do { if (tid == 0) { long long t_ = clock64(); ph[k] += t_ - tlast; tlast = t_; } } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
 
 // Byte offset of (context, slot) in the shared-memory state table. With 32 states per context every row starts on the
 // same 8 banks as the row four contexts further, so the word inside the row is XOR-swizzled with context bits 2..4:
@@ -184,6 +195,19 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
         for (int i = tid; i < 5 * 256; i += kModelThreads) S.qtab[i] = A.qtab[i];
         for (int i = tid; i < 512; i += kModelThreads) S.trans[i] = A.trans[i];
         for (int i = tid; i < (int)align16((size_t)A.nctx); i += kModelThreads) S.cnt8[i] = 0;
+        // t2[bit << 8 | state] = next state | record << 16: one lookup per bin gives the transition and the coder record
+        for (int i = tid; i < 512; i += kModelThreads) {
+            const uint32_t st = i & 255, bit = i >> 8;
+            S.t2[i] = (uint32_t)A.trans[i] | (make_rec(st, bit) << 16);
+        }
+        // slot of bin b of a symbol with exponent e (rangecoder::s, FFV1_RangeCoder.cpp:135-171): zero flag (slot 0), unary
+        // exponent (1..10), mantissa from the top bit down (22..31), sign (11..21)
+        for (int i = tid; i < 17 * kSlutRow; i += kModelThreads) {
+            const int e = i / kSlutRow, b = i % kSlutRow;
+            int slot = b <= e + 1 ? min(b, 10) : (b <= 2 * e + 1 ? 22 + min(2 * e + 1 - b, 9) : 11 + min(e, 10));
+            if (compact) slot = slot - (slot > 10) - 2 * (slot > 21);
+            S.slut[i] = (uint8_t)slot;
+        }
     }
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
@@ -240,6 +264,9 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     const int li = isB ? lane - 1 : isD ? lane - 11 : lane - 22;
     const int lslot = compact ? lane - (lane > 10) - 2 * (lane > 21) : lane;
     unsigned long long bins_total = 0;
+#ifdef B200_PHASE_TIMING
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
 
     for (int y = r0; y < r1; y++) {
         // software prefetch of the next payload row into registers; it lands in the ring after this row is coded
@@ -301,6 +328,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 }
             }
             __syncthreads();
+            PHASE_MARK(0);
             // ---- phase B1: exclusive prefix over chunks of the class counts (warp q: class q) and of the record totals (warp 0)
             {
                 const int q = warp;
@@ -331,6 +359,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 }
             }
             __syncthreads();
+            PHASE_MARK(1);
             // ---- phase B2: final record offsets; samples partitioned by owner warp, x order kept
             const uint32_t total = S.misc[0];
             {
@@ -352,6 +381,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 }
             }
             __syncthreads();
+            PHASE_MARK(2);
             // ---- phase C: warp q ranks the samples of its context class: round = occurrences of the context earlier in the row
             {
                 const uint32_t n = S.clstot[warp], base = S.cstart[warp];
@@ -380,50 +410,84 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 for (uint32_t i0 = lane; i0 < n; i0 += 32) S.cnt8[S.ctx[S.plist[base + i0]]] = 0;
             }
             __syncthreads();
-            // ---- phase D (K3): one sample per lane, all its bins; round by round (contexts inside a round are distinct)
+            PHASE_MARK(3);
+            // ---- phase D (K3): two samples per lane (independent chains, interleaved), all their bins; round by round (contexts
+            // inside a round are distinct, so the order inside a round is free)
             for (int r = 0; r < kRounds; r++) {
                 const uint32_t nr = S.rfill[r];
                 if (nr == 0) break;
-                for (uint32_t i0 = (uint32_t)warp * 32; i0 < nr; i0 += kModelThreads) {
-                    const bool act = i0 + lane < nr;
-                    uint32_t nb = 0, e = 0, o = 0, sgnslot = 0;
-                    uint64_t bw = 0;
-                    uint32_t cxd = 0;
-                    if (act) {
-                        const uint32_t x = S.rlist[rl_off[r] + i0 + lane];
-                        const int v = S.val[x];
-                        o = S.off[x];
-                        cxd = S.ctx[x];
-                        const uint32_t a = (uint32_t)abs(v);
-                        if (v == 0) { nb = 1; bw = 1; }
-                        else {
-                            e = 31 - __clz(a);
-                            nb = 2 * e + 3;
-                            const uint32_t mant = e ? (__brev(a & ((1u << e) - 1u)) >> (32 - e)) : 0u;   // bit i of a -> bit e-1-i
-                            bw = (uint64_t)(((1u << e) - 1u) << 1) | ((uint64_t)mant << (e + 2)) | ((uint64_t)(v < 0) << (2 * e + 2));
-                            sgnslot = 11 + min(e, 10u);
+                for (uint32_t i0 = (uint32_t)warp * 64; i0 < nr; i0 += kModelThreads * 2) {
+                    uint32_t nb[2] = {0, 0}, o[2] = {0, 0}, lo[2] = {0, 0}, hi[2] = {0, 0}, sbase[2] = {0, 0}, swz[2] = {0, 0};
+                    uint32_t lw[2][9];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const uint32_t j = i0 + q * 32 + lane;
+                        uint32_t e = 0;
+                        if (j < nr) {
+                            const uint32_t x = S.rlist[rl_off[r] + j];
+                            const int v = S.val[x];
+                            const uint32_t cxd = S.ctx[x];
+                            o[q] = S.off[x];
+                            sbase[q] = compact ? cxd * 27u : cxd * 32u;
+                            swz[q] = compact ? 0u : ((cxd >> 2) & 7u) << 2;
+                            const uint32_t a = (uint32_t)abs(v);
+                            if (v == 0) { nb[q] = 1; lo[q] = 1; }
+                            else {
+                                e = 31 - __clz(a);
+                                nb[q] = 2 * e + 3;
+                                const uint32_t mant = e ? (__brev(a & ((1u << e) - 1u)) >> (32 - e)) : 0u;   // bit i of a -> bit e-1-i
+                                const uint64_t bw = (uint64_t)(((1u << e) - 1u) << 1) | ((uint64_t)mant << (e + 2)) | ((uint64_t)(v < 0) << (2 * e + 2));
+                                lo[q] = (uint32_t)bw; hi[q] = (uint32_t)(bw >> 32);
+                            }
                         }
+                        const uint32_t* lrow = reinterpret_cast<const uint32_t*>(S.slut + e * kSlutRow);
+#pragma unroll
+                        for (int k = 0; k < 9; k++) lw[q][k] = lrow[k];
                     }
-                    const uint32_t nbmax = __reduce_max_sync(0xffffffffu, nb);
-                    for (uint32_t b = 0; b < nbmax; b++) {
-                        if (b < nb) {
-                            // bins 0..e+1: zero flag and unary exponent (slots 0, 1..10); then mantissa (22..31) from the top bit down,
-                            // last the sign (11..21)
-                            const uint32_t t = nb - 1 - b;
-                            uint32_t slot = b <= e + 1 ? min(b, 10u) : (t == 0 ? sgnslot : 21u + min(t, 10u));
-                            if (compact) slot = slot - (slot > 10) - 2 * (slot > 21);
-                            const uint32_t bit = (uint32_t)(bw >> b) & 1u;
-                            uint8_t* sp = S.states + state_off(cxd, slot, compact);
-                            const uint32_t st = *sp;
-                            *sp = S.trans[(bit << 8) | st];
-                            const uint32_t rec = make_rec(st, bit);
-                            const uint32_t idx = o + b;
-                            if (idx < stage_cap) S.stage[idx] = (uint16_t)rec; else out[idx] = (uint16_t)rec;
+                    const uint32_t nbmax = __reduce_max_sync(0xffffffffu, max(nb[0], nb[1]));
+                    const bool fits = __all_sync(0xffffffffu, o[0] + nb[0] <= stage_cap && o[1] + nb[1] <= stage_cap);
+                    uint8_t* sb0 = S.states + sbase[0];
+                    uint8_t* sb1 = S.states + sbase[1];
+                    if (fits) {
+                        uint16_t* so0 = S.stage + o[0];
+                        uint16_t* so1 = S.stage + o[1];
+#pragma unroll
+                        for (uint32_t b = 0; b < 35; b++) {
+                            if (b >= nbmax) break;
+                            const bool p0 = b < nb[0], p1 = b < nb[1];
+                            uint8_t* s0 = sb0 + (((lw[0][b >> 2] >> ((b & 3) * 8)) & 255u) ^ swz[0]);
+                            uint8_t* s1 = sb1 + (((lw[1][b >> 2] >> ((b & 3) * 8)) & 255u) ^ swz[1]);
+                            uint32_t st0 = 0, st1 = 0;
+                            if (p0) st0 = *s0;
+                            if (p1) st1 = *s1;
+                            const uint32_t bit0 = b < 32 ? (lo[0] >> b) & 1u : (hi[0] >> (b - 32)) & 1u;
+                            const uint32_t bit1 = b < 32 ? (lo[1] >> b) & 1u : (hi[1] >> (b - 32)) & 1u;
+                            const uint32_t t0 = S.t2[(bit0 << 8) | st0];
+                            const uint32_t t1 = S.t2[(bit1 << 8) | st1];
+                            if (p0) { *s0 = (uint8_t)t0; so0[b] = (uint16_t)(t0 >> 16); }
+                            if (p1) { *s1 = (uint8_t)t1; so1[b] = (uint16_t)(t1 >> 16); }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            uint8_t* sbq = q ? sb1 : sb0;
+                            for (uint32_t b = 0; b < nbmax; b++) {
+                                if (b < nb[q]) {
+                                    const uint32_t e = (nb[q] - 3) >> 1;
+                                    uint8_t* sp = sbq + ((nb[q] == 1 ? 0u : (uint32_t)S.slut[e * kSlutRow + b]) ^ swz[q]);
+                                    const uint32_t bit = b < 32 ? (lo[q] >> b) & 1u : (hi[q] >> (b - 32)) & 1u;
+                                    const uint32_t tt = S.t2[(bit << 8) | *sp];
+                                    *sp = (uint8_t)tt;
+                                    const uint32_t idx = o[q] + b;
+                                    if (idx < stage_cap) S.stage[idx] = (uint16_t)(tt >> 16); else out[idx] = (uint16_t)(tt >> 16);
+                                }
+                            }
                         }
                     }
                 }
                 __syncthreads();
             }
+            PHASE_MARK(4);
             // ---- phase E: samples beyond kRounds occurrences of their context (flat areas): the owner warp walks them in x order,
             // one sample per step, lane s = slot s of the context (slots are independent chains)
             if (S.rfill[kRounds]) {
@@ -481,6 +545,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 }
                 __syncthreads();
             }
+            PHASE_MARK(5);
             // ---- phase F: staged records -> global, coalesced; pad the segment to a whole 128-byte block with no-op records
             {
                 const uint32_t ns = min(total, stage_cap);
@@ -493,6 +558,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 } else {
                     for (uint32_t i = tid; i < ns; i += kModelThreads) out[i] = S.stage[i];
                 }
+                PHASE_MARK(7);
                 const uint32_t seg_len = seg_extra + total;
                 const uint32_t pad = ((seg_len + 63u) & ~63u) - seg_len;
                 if (tid < (int)pad) out[total + tid] = (uint16_t)kNopRec;
@@ -502,6 +568,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 bins_total += total;
             }
             __syncthreads();
+            PHASE_MARK(6);
         }
         if (have_next) {
             int32_t* dst = S.ring + (size_t)((y + 4) % 3) * planes * wmax;
@@ -512,7 +579,11 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
             }
             __syncthreads();
         }
+        PHASE_MARK(7);
     }
+#ifdef B200_PHASE_TIMING
+    if (tid == 0) for (int k = 0; k < 8; k++) atomicAdd(reinterpret_cast<unsigned long long*>(A.flags + 16) + k, (unsigned long long)ph[k]);
+#endif
     if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(A.flags + 2), bins_total);
     if (r1 < g.h) {   // carry the states to the next band
         const int n16 = state_bytes >> 4;
