@@ -112,7 +112,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     A.wmax = wmax; A.hmax = hmax;
     A.sstride = S.sbits <= 9 ? 27 : 32;
 
-    if (wmax > 4 * b200::kModelThreads) { delete E; return fail(B200_ERR_INVALID, "slice wider than 2048 pixels: use more slices"); }
+    if (wmax > 2048) { delete E; return fail(B200_ERR_INVALID, "slice wider than 2048 pixels: use more slices"); }
     // the model kernel keeps the whole context-state table of one plane-set in shared memory
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);

@@ -106,7 +106,7 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes) {
     n += align16((size_t)wmax * 2) * 2;          // ctx, plist
     n += align16((size_t)nctx);                  // cnt8
     n += align16((size_t)wmax);                  // tmp8
-    n += kMaxChunks * 16 * 2 + kMaxChunks * 4 + 32 * 2 + 32 * 2;   // ccnt, ctot, clstot, cstart
+    n += kMaxChunks * kModelWarps * 2 + kMaxChunks * 4 + 32 * 2 + 32 * 2;   // ccnt, ctot, clstot, cstart
     n += align16((size_t)rlist_entries(wmax) * 2);
     n += 16 * 4 + 16 * 4;                        // rfill, misc
     n += 5 * 256 * 2 + 512 + kSlutBytes + 512 * 4;
@@ -126,7 +126,7 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     m.plist = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
     m.cnt8 = base; base += align16((size_t)nctx);
     m.tmp8 = base; base += align16((size_t)wmax);
-    m.ccnt = reinterpret_cast<uint16_t*>(base); base += kMaxChunks * 16 * 2;
+    m.ccnt = reinterpret_cast<uint16_t*>(base); base += kMaxChunks * kModelWarps * 2;
     m.ctot = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * 4;
     m.clstot = reinterpret_cast<uint16_t*>(base); base += 32 * 2;
     m.cstart = reinterpret_cast<uint16_t*>(base); base += 32 * 2;
@@ -146,7 +146,7 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
 // 128-byte blocks.
 __device__ __forceinline__ uint32_t make_rec(uint32_t st, uint32_t bit) { return (bit ? st : 256u - st) | (bit << 9); }
 
-constexpr int kMaxPixPerThread = 4;      // wmax <= 4 * kModelThreads
+constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     constexpr int NW = kModelThreads / 32;
-    static_assert(NW == 16, "context classes are ctx & 15");
+    static_assert(NW == 16 || NW == 32, "context class = ctx & (NW - 1) = owner warp");
     ModelSmem S = carve(smem_raw, A.nctx, A.sstride, wmax, planes);
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
     const bool compact = A.sstride != 32;   // 8-bit streams never use slots 10, 20, 21, 30, 31 (e <= 8): 27 states per context
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                 const int c = warp * KC + k;
                 const int x = c * 32 + lane;
                 const bool valid = x < w;
-                uint32_t nb = 0, cls = 16 + lane;
+                uint32_t nb = 0, cls = 32 + lane;
                 if (valid) {
                     const int T = prv[x];
                     const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
@@ -309,14 +309,14 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                     S.val[x] = d;
                     S.ctx[x] = (uint16_t)ctx;
                     nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
-                    cls = (uint32_t)ctx & 15u;
+                    cls = (uint32_t)ctx & (uint32_t)(NW - 1);
                 }
                 uint32_t incl = nb;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
                 const uint32_t m = __match_any_sync(0xffffffffu, cls);
                 if (c < kMaxChunks) {
-                    if (lane < 16) S.ccnt[c * 16 + lane] = 0;
+                    if (lane < NW) S.ccnt[c * NW + lane] = 0;
                     if (lane == 31) S.ctot[c] = incl;
                 }
                 __syncwarp();
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                     S.off[x] = incl - nb;                                      // chunk-relative for now
                     const uint32_t intra = __popc(m & lt);
                     S.tmp8[x] = (uint8_t)intra;
-                    if (intra == 0) S.ccnt[c * 16 + cls] = (uint16_t)__popc(m);
+                    if (intra == 0) S.ccnt[c * NW + cls] = (uint16_t)__popc(m);
                 }
             }
             __syncthreads();
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
             {
                 const int q = warp;
                 const int c0 = lane, c1 = lane + 32;
-                uint32_t v0 = c0 < nchunk ? S.ccnt[c0 * 16 + q] : 0u, v1 = c1 < nchunk ? S.ccnt[c1 * 16 + q] : 0u;
+                uint32_t v0 = c0 < nchunk ? S.ccnt[c0 * NW + q] : 0u, v1 = c1 < nchunk ? S.ccnt[c1 * NW + q] : 0u;
                 uint32_t i0 = v0, i1 = v1;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                     if (lane >= o) { i0 += t0; i1 += t1; }
                 }
                 const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-                if (c0 < nchunk) S.ccnt[c0 * 16 + q] = (uint16_t)(i0 - v0);
-                if (c1 < nchunk) S.ccnt[c1 * 16 + q] = (uint16_t)(tot0 + i1 - v1);
+                if (c0 < nchunk) S.ccnt[c0 * NW + q] = (uint16_t)(i0 - v0);
+                if (c1 < nchunk) S.ccnt[c1 * NW + q] = (uint16_t)(tot0 + i1 - v1);
                 if (lane == 0) S.clstot[q] = (uint16_t)(tot0 + tot1);
                 if (warp == 0) {
                     uint32_t a0 = c0 < nchunk ? S.ctot[c0] : 0u, a1 = c1 < nchunk ? S.ctot[c1] : 0u;
@@ -363,20 +363,20 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
             // ---- phase B2: final record offsets; samples partitioned by owner warp, x order kept
             const uint32_t total = S.misc[0];
             {
-                uint32_t ct = lane < 16 ? S.clstot[lane] : 0u, ci = ct;
+                uint32_t ct = lane < NW ? S.clstot[lane] : 0u, ci = ct;
 #pragma unroll
-                for (int o = 1; o < 16; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ci, o); if (lane >= o) ci += t; }
+                for (int o = 1; o < NW; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ci, o); if (lane >= o) ci += t; }
                 const uint32_t cst = ci - ct;                                   // lane q < 16: first plist entry of class q
-                if (warp == 0 && lane < 16) S.cstart[lane] = (uint16_t)cst;
+                if (warp == 0 && lane < NW) S.cstart[lane] = (uint16_t)cst;
                 for (int k = 0; k < KC; k++) {
                     const int c = warp * KC + k;
                     const int x = c * 32 + lane;
                     const bool valid = x < w;
-                    const uint32_t cls = valid ? (S.ctx[x] & 15u) : 0u;
+                    const uint32_t cls = valid ? (S.ctx[x] & (uint32_t)(NW - 1)) : 0u;
                     const uint32_t base = __shfl_sync(0xffffffffu, cst, cls);
                     if (valid) {
                         S.off[x] += S.ctot[c];
-                        S.plist[base + S.ccnt[c * 16 + cls] + S.tmp8[x]] = (uint16_t)x;
+                        S.plist[base + S.ccnt[c * NW + cls] + S.tmp8[x]] = (uint16_t)x;
                     }
                 }
             }

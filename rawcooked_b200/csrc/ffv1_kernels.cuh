@@ -19,7 +19,11 @@
 
 namespace b200 {
 
-constexpr int kModelThreads = 512;     // 16 warps: one CTA per SM when the large context model (162 KB) is in smem
+#ifndef B200_MODEL_THREADS
+#define B200_MODEL_THREADS 512
+#endif
+constexpr int kModelThreads = B200_MODEL_THREADS;   // one CTA per SM when the large context model (162 KB) is in smem
+constexpr int kModelWarps = kModelThreads / 32;
 constexpr int kMaxHeaderBins = 96;
 
 // persistent range-coder registers of one slice between bands
