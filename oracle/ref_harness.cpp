@@ -69,3 +69,54 @@ void ref_default_state_transitions(uint8_t out[256]) { memcpy(out, default_state
 uint32_t ref_crc32(const uint8_t* data, size_t size) { return ZenCRC32(data, size); }
 
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FLAC: the reference's vendored libFLAC 1.3.2 decoder (Source/Lib/ThirdParty/flac), driven like flac_wrapper does
+// (Source/Lib/CoDec/Wrapper.cpp:138-219: CodecPrivate first, then one frame per SimpleBlock).
+#include "FLAC/stream_decoder.h"
+namespace {
+struct flac_mem {
+    const uint8_t* data; size_t size, pos;
+    int32_t* out; size_t cap, n;      // interleaved samples
+    unsigned channels, bps; int error;
+};
+FLAC__StreamDecoderReadStatus flac_read(const FLAC__StreamDecoder*, FLAC__byte buffer[], size_t* bytes, void* client) {
+    flac_mem* m = (flac_mem*)client;
+    size_t left = m->size - m->pos;
+    if (!left) { *bytes = 0; return FLAC__STREAM_DECODER_READ_STATUS_END_OF_STREAM; }
+    if (*bytes > left) *bytes = left;
+    memcpy(buffer, m->data + m->pos, *bytes);
+    m->pos += *bytes;
+    return FLAC__STREAM_DECODER_READ_STATUS_CONTINUE;
+}
+FLAC__StreamDecoderWriteStatus flac_write(const FLAC__StreamDecoder*, const FLAC__Frame* frame, const FLAC__int32* const buffer[], void* client) {
+    flac_mem* m = (flac_mem*)client;
+    m->channels = frame->header.channels; m->bps = frame->header.bits_per_sample;
+    for (unsigned i = 0; i < frame->header.blocksize; i++)
+        for (unsigned c = 0; c < frame->header.channels; c++) {
+            if (m->n < m->cap) m->out[m->n] = buffer[c][i];
+            m->n++;
+        }
+    return FLAC__STREAM_DECODER_WRITE_STATUS_CONTINUE;
+}
+void flac_error(const FLAC__StreamDecoder*, FLAC__StreamDecoderErrorStatus, void* client) { ((flac_mem*)client)->error++; }
+}  // namespace
+
+extern "C" {
+// stream = CodecPrivate ("fLaC" + STREAMINFO) followed by the frames. Returns 0 ok; out_n = samples decoded (all channels).
+int ref_flac_decode(const uint8_t* stream, size_t size, int32_t* out, size_t cap, size_t* out_n, unsigned* channels, unsigned* bps)
+{
+    flac_mem m = {stream, size, 0, out, cap, 0, 0, 0, 0};
+    FLAC__StreamDecoder* d = FLAC__stream_decoder_new();
+    if (!d) return 3;
+    FLAC__stream_decoder_set_md5_checking(d, true);
+    if (FLAC__stream_decoder_init_stream(d, flac_read, 0, 0, 0, 0, flac_write, 0, flac_error, &m) != FLAC__STREAM_DECODER_INIT_STATUS_OK) { FLAC__stream_decoder_delete(d); return 3; }
+    FLAC__bool ok = FLAC__stream_decoder_process_until_end_of_stream(d);
+    FLAC__stream_decoder_finish(d);
+    FLAC__stream_decoder_delete(d);
+    if (out_n) *out_n = m.n;
+    if (channels) *channels = m.channels;
+    if (bps) *bps = m.bps;
+    return (!ok || m.error) ? 1 : (m.n > m.cap ? 2 : 0);
+}
+}

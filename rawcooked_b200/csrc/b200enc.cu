@@ -32,6 +32,8 @@ cudaError_t dalloc(T** p, size_t n, std::vector<void*>& owned) {
 
 }  // namespace
 
+void b200_set_error(const std::string& msg) { g_err = msg; }
+
 struct b200_ffv1_enc {
     b200_ffv1_cfg cfg;
     b200::Ffv1Stream st;

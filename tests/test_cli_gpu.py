@@ -1,0 +1,68 @@
+"""End-to-end drop-in test (GPU): the UNMODIFIED reference CLI (oracle/_ref/rawcooked) analyses the inputs, writes its
+reversibility sidecar, launches OUR encoder through --bin-name exactly where it would launch ffmpeg
+(/root/reference/Source/CLI/Output.cpp:356), then runs its own `--check` on the MKV we wrote. The test passes when the
+reference prints "Reversibility was checked, no issue detected." — the same success string its test suite greps for
+(Project/GNU/CLI/test/test2.sh:37)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from rawcooked_b200 import synth as S
+
+pytestmark = pytest.mark.gpu
+B200ENC = os.path.join(util.ROOT, "rawcooked_b200", "b200enc")
+OK = "Reversibility was checked, no issue detected."
+
+
+def run_rawcooked(args, cwd):
+    rc = util.ref_rawcooked()
+    if rc is None:
+        pytest.skip("oracle/_ref/rawcooked not built")
+    p = subprocess.run([rc] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    return p.returncode, p.stdout + p.stderr
+
+
+def write_dpx_sequence(d, n, w, h, layout, seed0):
+    os.makedirs(d, exist_ok=True)
+    for i in range(n):
+        payload = S.synth_payload(w, h, layout, seed0 + i, "grain")
+        open(os.path.join(d, "f_%06d.dpx" % i), "wb").write(S.dpx_file(w, h, layout, payload, i))
+
+
+@pytest.mark.parametrize("name,w,h,layout,n,extra", [
+    ("config1_8bit", 640, 480, S.DPX_RGB_8, 10, []),                          # BASELINE config 1
+    ("rgb10", 256, 192, S.DPX_RGB_10_FA_BE, 4, ["-slices", "4"]),
+    ("rgb12packed", 264, 100, S.DPX_RGB_12_PACKED_BE, 3, []),
+    ("rgb16", 320, 240, S.DPX_RGB_16_BE, 5, ["-slices", "24"]),
+])
+def test_rawcooked_all_with_b200enc(tmp_path, name, w, h, layout, n, extra):
+    seq = tmp_path / name
+    write_dpx_sequence(str(seq), n, w, h, layout, 1000)
+    code, out = run_rawcooked(["--all", "-y", "-b", B200ENC] + extra + [name], cwd=str(tmp_path))
+    assert code == 0, out
+    assert OK in out, out
+    mkv = tmp_path / (name + ".mkv")
+    assert mkv.exists() and mkv.stat().st_size > 1000
+    # the check must be a real one: flip one payload byte in a source frame and re-check the MKV against the files
+    victim = seq / "f_000002.dpx"
+    b = bytearray(victim.read_bytes())
+    b[4000] ^= 0x10
+    victim.write_bytes(bytes(b))
+    code2, out2 = run_rawcooked(["--check", name + ".mkv", "-o", "./"], cwd=str(tmp_path))
+    assert OK not in out2 and ("not same" in out2 or code2 != 0), out2
+
+
+def test_rawcooked_dpx_plus_wav(tmp_path):
+    # video + audio in one package: FFV1 + FLAC together (BASELINE config 4 in small)
+    name = "pkg"
+    seq = tmp_path / name
+    write_dpx_sequence(str(seq), 6, 320, 240, S.DPX_RGB_16_BE, 50)
+    pcm = S.wav_pcm(2, 48000, 24, 12000, 77)
+    open(seq / "audio.wav", "wb").write(S.wav_file(pcm, 48000, 24))
+    code, out = run_rawcooked(["--all", "-y", "-b", B200ENC, name], cwd=str(tmp_path))
+    assert code == 0, out
+    assert OK in out, out

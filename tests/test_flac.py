@@ -1,0 +1,133 @@
+"""FLAC path: the oracle (oracle/flac_oracle.c) is pinned by decoding every frame with the reference's vendored libFLAC
+(oracle/_ref) back to the input PCM; on the GPU the CUDA frames must equal the oracle's byte for byte."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from rawcooked_b200 import synth as S
+
+needs_ref = pytest.mark.skipif(not util.ref_available(), reason="oracle/_ref not built")
+_flac = None
+
+
+def flac_oracle():
+    global _flac
+    if _flac is None:
+        so = os.path.join(util.ORACLE_DIR, "libflac_oracle.so")
+        src = os.path.join(util.ORACLE_DIR, "flac_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", util.ORACLE_DIR, "libflac_oracle.so"], stdout=subprocess.DEVNULL)
+        O = C.CDLL(so)
+        O.flaco_encode_frame.restype = C.c_size_t
+        O.flaco_encode_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_size_t]
+        O.flaco_codec_private.restype = C.c_size_t
+        O.flaco_codec_private.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+        _flac = O
+    return _flac
+
+
+def oracle_frames(pcm, sr, bits, first_frame=0):
+    O = flac_oracle()
+    n, ch = pcm.shape
+    bs = O.flaco_blocksize(sr)
+    cap = bs * ch * 4 + 1024
+    buf = np.zeros(cap, np.uint8)
+    frames = []
+    for f, i in enumerate(range(0, n, bs)):
+        blk = np.ascontiguousarray(pcm[i:i + bs], dtype=np.int32)
+        m = O.flaco_encode_frame(blk.ctypes.data, len(blk), ch, bits, sr, bs, first_frame + f, buf.ctypes.data, cap)
+        assert m > 0
+        frames.append(buf[:m].tobytes())
+    return frames, bs
+
+
+def oracle_private(bs, frames, sr, ch, bits, n):
+    cp = (C.c_uint8 * 42)()
+    flac_oracle().flaco_codec_private(bs, min(len(f) for f in frames), max(len(f) for f in frames), sr, ch, bits, n, cp)
+    return bytes(cp)
+
+
+def ref_decode(private, frames, n, ch):
+    R = util.ref_decoder()
+    R.ref_flac_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    stream = private + b"".join(frames)
+    out = np.zeros(n * ch + 64, np.int32)
+    on, c, b = C.c_size_t(0), C.c_uint(0), C.c_uint(0)
+    rc = R.ref_flac_decode(stream, len(stream), out.ctypes.data, out.size, C.byref(on), C.byref(c), C.byref(b))
+    assert rc == 0, "reference libFLAC rejected the stream (rc=%d)" % rc
+    assert on.value == n * ch
+    return out[:n * ch].reshape(n, ch)
+
+
+def make_pcm(ch, sr, bits, n, kind, seed=77):
+    if kind == "noise":
+        return np.random.default_rng(seed).integers(-(1 << (bits - 1)), 1 << (bits - 1), (n, ch)).astype(np.int32)
+    if kind == "zero":
+        return np.zeros((n, ch), np.int32)
+    if kind == "dc":
+        return np.full((n, ch), 1234 % (1 << (bits - 1)), np.int32)
+    if kind == "extreme":
+        p = np.zeros((n, ch), np.int32)
+        p[::2] = (1 << (bits - 1)) - 1
+        p[1::2] = -(1 << (bits - 1))
+        return p
+    return S.wav_pcm(ch, sr, bits, n, seed)
+
+
+CASES = [(2, 48000, 16, 20000, "sine"), (6, 96000, 24, 30000, "sine"), (1, 44100, 8, 5000, "sine"), (2, 48000, 24, 9316, "noise"),
+         (2, 48000, 16, 10000, "zero"), (1, 8000, 16, 7, "sine"), (3, 32000, 16, 3000, "sine"), (2, 11025, 16, 3000, "sine"),
+         (2, 48000, 16, 4608, "dc"), (2, 96000, 24, 8192 + 15, "extreme"), (8, 48000, 16, 5000, "sine"), (1, 192000, 24, 40000, "sine")]
+
+
+@needs_ref
+@pytest.mark.parametrize("ch,sr,bits,n,kind", CASES)
+def test_oracle_decodes_through_reference_libflac(ch, sr, bits, n, kind):
+    pcm = make_pcm(ch, sr, bits, n, kind)
+    frames, bs = oracle_frames(pcm, sr, bits)
+    assert bs <= 16384                                   # reference buffers at most 16384 samples per block (Wrapper.cpp:251)
+    dec = ref_decode(oracle_private(bs, frames, sr, ch, bits, n), frames, n, ch)
+    assert np.array_equal(dec, pcm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch,sr,bits,n,kind", CASES)
+def test_cuda_flac_matches_oracle_and_reference(ch, sr, bits, n, kind):
+    from rawcooked_b200 import flac
+    pcm = make_pcm(ch, sr, bits, n, kind)
+    enc = flac.FLACEncoder(sr, ch, bits, max_blocks=3)      # small max_blocks: several encode calls, frame numbers carry on
+    try:
+        frames = enc.encode(flac.pcm_to_wav_bytes(pcm, bits))
+        want, bs = oracle_frames(pcm, sr, bits)
+        assert enc.block_size == bs
+        assert len(frames) == len(want)
+        for i, (a, b) in enumerate(zip(frames, want)):
+            assert a == b, "frame %d differs from the oracle" % i
+        private = enc.codec_private()
+        assert private == oracle_private(bs, want, sr, ch, bits, n)
+        if util.ref_available():
+            assert np.array_equal(ref_decode(private, frames, n, ch), pcm)
+    finally:
+        enc.close()
+
+
+@pytest.mark.gpu
+def test_config4_audio_six_channels_96k_24bit():
+    # the audio half of BASELINE config 4: 24-bit / 96 kHz / 6 channels, a few seconds
+    from rawcooked_b200 import flac
+    ch, sr, bits, n = 6, 96000, 24, 96000 * 3
+    pcm = S.wav_pcm(ch, sr, bits, n, 77)
+    enc = flac.FLACEncoder(sr, ch, bits)
+    try:
+        frames = enc.encode(flac.pcm_to_wav_bytes(pcm, bits))
+        assert enc.block_size == 8192
+        want, _ = oracle_frames(pcm, sr, bits)
+        assert frames == want
+        if util.ref_available():
+            assert np.array_equal(ref_decode(enc.codec_private(), frames, n, ch), pcm)
+        assert sum(len(f) for f in frames) < 0.8 * n * ch * 3
+    finally:
+        enc.close()
