@@ -112,32 +112,48 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     if (A.band_rows > hmax) A.band_rows = hmax;
     A.nbands = (hmax + A.band_rows - 1) / A.band_rows;
     A.wmax = wmax; A.hmax = hmax;
-    A.sstride = S.sbits <= 9 ? 27 : 32;
+    A.sstride = S.sbits <= 9 ? 28 : 32;
 
     if (wmax > 2048) { delete E; return fail(B200_ERR_INVALID, "slice wider than 2048 pixels: use more slices"); }
-    // the model kernel keeps the whole context-state table of one plane-set in shared memory
+    // The model kernel keeps the whole context-state table of one plane-set in shared memory; what is left (minus a
+    // reserve that lets k_range CTAs run on the same SM) stages the records of one plane-row. Rows whose records do not fit are
+    // coded in up to kMaxSeg column segments. Three layouts of the small tables, tried from the fastest to the leanest:
+    // replicated one_state table + direct first-occurrence table, replicated + hashed, plain + hashed.
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     const int maxbins = 2 * S.sbits + 1;                        // bins of the largest symbol: 2e+3 with e = sbits-1
-    size_t fixed = b200::model_smem_fixed(S.nctx, A.sstride, wmax, 2);
-    if (fixed + 4096 > (size_t)dev_smem) {
+    const size_t row_need = (((size_t)wmax * maxbins + b200::kMaxHeaderBins) + 127) & ~(size_t)127;
+    const size_t chunk_need = 32 * (size_t)maxbins + b200::kMaxHeaderBins;
+    const int tries[3] = {A.sstride == 32 ? S.nctx : 0, 2048, -2048};
+    int best = -1, best_nseg = 0;
+    size_t best_cap = 0;
+    for (int k = 0; k < 3; k++) {
+        if (!tries[k]) continue;
+        const size_t fixed = b200::model_smem_fixed(S.nctx, A.sstride, wmax, 2, tries[k]);
+        if (fixed + (size_t)b200::kModelSmemReserve + 2 * (chunk_need + 256) > (size_t)dev_smem) continue;
+        size_t capk = (((size_t)dev_smem - b200::kModelSmemReserve - fixed) / 2) & ~(size_t)127;
+        if (capk > row_need) capk = row_need;
+        const int nsegk = capk >= row_need ? 1 : (int)(((size_t)wmax * maxbins + (capk - chunk_need) - 1) / (capk - chunk_need));
+        if (capk > best_cap) { best = k; best_nseg = nsegk; best_cap = capk; }
+        if (capk * 10 >= row_need * 6) break;      // good enough: typical rows are far below the worst case
+    }
+    if (best < 0 || best_nseg > b200::kMaxSeg) {
         delete E;
-        char buf[200];
-        snprintf(buf, sizeof buf, "slice too wide for the shared-memory context model (%zu B needed, %d available): use more slices", fixed + 4096, dev_smem);
-        return fail(B200_ERR_INVALID, buf);
+        return fail(B200_ERR_INVALID, "slice too wide for the shared-memory context model: use more slices");
     }
-    {   // whatever shared memory is left stages the records of a plane-row (rows that need more spill straight to global)
-        size_t room = ((size_t)dev_smem - fixed) / 2;
-        size_t want = (size_t)wmax * maxbins;
-        A.stage_cap = (int32_t)((room < want ? room : want) & ~(size_t)7);
-    }
-    cudaError_t ce = b200::configure_kernels(S.nctx, A.sstride, wmax, A.stage_cap);
+    A.first_n = tries[best];
+    A.stage_cap = (int32_t)best_cap;
+    A.nseg = best_nseg;
+    if (A.band_rows * 3 * A.nseg > 4096) { delete E; return fail(B200_ERR_INVALID, "band too large"); }
+    cudaError_t ce = b200::configure_kernels(A);
     if (ce != cudaSuccess) { delete E; return fail_cuda(ce, "configure_kernels"); }
 
-    A.capY = ((size_t)A.band_rows * ((size_t)wmax * maxbins + 64) + b200::kMaxHeaderBins + 63) & ~(size_t)63;   // + block padding per plane-row
+    // records of one band of one slice: every plane-row segment is padded to whole 128-record blocks
+    A.capY = (size_t)A.band_rows * (row_need + 128 * (size_t)A.nseg) + 128;
     A.capC = A.capY * 2;
     size_t samples = (size_t)wmax * hmax * 3;
-    A.slice_cap = ((samples * (2 * S.bits + 5) / 8 + 1024 + 15) & ~(size_t)15);   // ffmpeg's own worst-case bound per sample
+    // slice byte streams: FFmpeg's own worst-case bound per sample (white noise on small 16-bit slices really reaches 1.7 x raw)
+    A.slice_cap = ((samples * (2 * S.bits + 5) / 8 + 1024 + 15) & ~(size_t)15);
     E->max_packet = A.slice_cap * ns;
     A.arena_cap = E->max_packet * B;
 
@@ -147,36 +163,40 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     for (int i = 0; i < ns; i++) {
         if (S.header_bins[i].size() > (size_t)b200::kMaxHeaderBins) { delete E; return fail(B200_ERR_INVALID, "slice header too long"); }
         hc[i] = (int32_t)S.header_bins[i].size();
-        for (size_t k = 0; k < S.header_bins[i].size(); k++) {      // (state | bit << 8) -> coder record sp | bit << 9
+        for (size_t k = 0; k < S.header_bins[i].size(); k++) {      // (state | bit << 8) -> coder record (sp - 1) | bit << 8
             const uint16_t r = S.header_bins[i][k];
             const uint32_t st = r & 255u, bit = r >> 8;
-            hb[(size_t)i * b200::kMaxHeaderBins + k] = (uint16_t)((bit ? st : 256u - st) | (bit << 9));
+            hb[(size_t)i * b200::kMaxHeaderBins + k] = (uint16_t)(((bit ? st : 256u - st) - 1u) | (bit << 8));
         }
     }
-    uint8_t trans[512];
-    std::memcpy(trans, S.zero_state, 256);
-    std::memcpy(trans + 256, S.one_state, 256);
+    uint8_t t1q[256];                                               // one_state indexed by q = sp - 1
+    for (int i = 0; i < 255; i++) t1q[i] = S.one_state[i + 1];
+    t1q[255] = 0;
 
     b200::SliceGeom* d_geom; int16_t* d_qtab; uint8_t* d_trans; uint16_t* d_hb; int32_t* d_hc; uint32_t* d_crc;
 #define ALLOC(p, n) do { cudaError_t e_ = dalloc(&(p), (n), own); if (e_ != cudaSuccess) { int rc_ = fail_cuda(e_, "cudaMalloc " #p); b200_ffv1_close(E); return rc_; } } while (0)
     ALLOC(d_geom, sizeof(b200::SliceGeom) * ns);
     ALLOC(d_qtab, sizeof S.qtab);
-    ALLOC(d_trans, 512);
+    ALLOC(d_trans, 256);
     ALLOC(d_hb, hb.size() * 2);
     ALLOC(d_hc, hc.size() * 4);
     ALLOC(d_crc, 1024);
     ALLOC(A.state_save, (size_t)B * ns * 2 * (((size_t)S.nctx * A.sstride + 15) & ~(size_t)15));
     b200::EncArgs& A1 = E->args1;
-    ALLOC(A.binsY, (size_t)B * ns * A.capY * 2);
-    ALLOC(A.binsC, (size_t)B * ns * A.capC * 2);
-    ALLOC(A.rowcnt, (size_t)B * ns * A.band_rows * 3 * 4);
+    ALLOC(A.qY, (size_t)B * ns * A.capY);
+    ALLOC(A.qC, (size_t)B * ns * A.capC);
+    ALLOC(A.bY, (size_t)B * ns * (A.capY >> 3));
+    ALLOC(A.bC, (size_t)B * ns * (A.capC >> 3));
+    ALLOC(A.rowcnt, (size_t)B * ns * A.band_rows * 3 * A.nseg * 4);
     ALLOC(A.ckptY, (size_t)B * ns * (A.capY >> 6) * 8);
     ALLOC(A.ckptC, (size_t)B * ns * (A.capC >> 6) * 8);
     ALLOC(A.used, (size_t)B * ns * 2 * 4);
-    uint16_t *bY1, *bC1; uint32_t *rc1, *us1; uint2 *kY1, *kC1;
-    ALLOC(bY1, (size_t)B * ns * A.capY * 2);
-    ALLOC(bC1, (size_t)B * ns * A.capC * 2);
-    ALLOC(rc1, (size_t)B * ns * A.band_rows * 3 * 4);
+    uint8_t *qY1, *qC1, *bY1, *bC1; uint32_t *rc1, *us1; uint2 *kY1, *kC1;
+    ALLOC(qY1, (size_t)B * ns * A.capY);
+    ALLOC(qC1, (size_t)B * ns * A.capC);
+    ALLOC(bY1, (size_t)B * ns * (A.capY >> 3));
+    ALLOC(bC1, (size_t)B * ns * (A.capC >> 3));
+    ALLOC(rc1, (size_t)B * ns * A.band_rows * 3 * A.nseg * 4);
     ALLOC(kY1, (size_t)B * ns * (A.capY >> 6) * 8);
     ALLOC(kC1, (size_t)B * ns * (A.capC >> 6) * 8);
     ALLOC(us1, (size_t)B * ns * 2 * 4);
@@ -191,16 +211,19 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
 #undef ALLOC
     cudaMemcpy(d_geom, S.slices.data(), sizeof(b200::SliceGeom) * ns, cudaMemcpyHostToDevice);
     cudaMemcpy(d_qtab, S.qtab, sizeof S.qtab, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_trans, trans, 512, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_trans, t1q, 256, cudaMemcpyHostToDevice);
     cudaMemcpy(d_hb, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(d_hc, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d_crc, b200::crc32_mpeg_table(), 1024, cudaMemcpyHostToDevice);
-    A.geom = d_geom; A.qtab = d_qtab; A.trans = d_trans; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
+    A.geom = d_geom; A.qtab = d_qtab; A.t1q = d_trans; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
     A1 = A;
-    A1.binsY = bY1; A1.binsC = bC1; A1.rowcnt = rc1; A1.ckptY = kY1; A1.ckptC = kC1; A1.used = us1;
-    cudaStreamCreateWithFlags(&E->sm, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&E->sr, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&E->se, cudaStreamNonBlocking);
+    A1.qY = qY1; A1.qC = qC1; A1.bY = bY1; A1.bC = bC1; A1.rowcnt = rc1; A1.ckptY = kY1; A1.ckptC = kC1; A1.used = us1;
+    // the serial coder and the emitter must never wait behind queued model CTAs: their streams get the higher priority
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&E->sm, cudaStreamNonBlocking, prio_lo);
+    cudaStreamCreateWithPriority(&E->sr, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&E->se, cudaStreamNonBlocking, prio_hi);
     for (cudaEvent_t* ev : {&E->ev_start, &E->ev_model[0], &E->ev_model[1], &E->ev_range[0], &E->ev_range[1], &E->ev_emit[0],
                             &E->ev_emit[1], &E->ev_done_m, &E->ev_done_e})
         cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -311,10 +334,11 @@ static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* 
     CU(cudaMemcpy(E->h_flags, A.flags, 256, cudaMemcpyDeviceToHost));
     if (getenv("B200_PHASE_TIMING")) {
         const unsigned long long* ph = reinterpret_cast<const unsigned long long*>(E->h_flags + 16);
-        fprintf(stderr, "k_model phase cycles (sum over CTAs): A %llu B1 %llu B2 %llu C %llu D %llu E %llu F %llu next-row %llu\n", ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+        fprintf(stderr, "k_model phase cycles (sum over CTAs): S1 %llu S2p %llu S2a %llu S2b %llu S3 %llu\n", ph[0], ph[1], ph[2], ph[3], ph[4]);
     }
     if (E->h_flags[0] & 1u) return fail(B200_ERR_OVERFLOW, "slice scratch overflow");
     if (E->h_flags[0] & 2u) return fail(B200_ERR_OVERFLOW, "packet arena overflow");
+    if (E->h_flags[0] & 4u) return fail(B200_ERR_OVERFLOW, "plane-row needs more column segments than reserved");
     CU(cudaMemcpy(E->h_off.data(), A.frame_off, (size_t)n_frames * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(E->h_len.data(), A.frame_len, (size_t)n_frames * 8, cudaMemcpyDeviceToHost));
     uint64_t tot = 0;

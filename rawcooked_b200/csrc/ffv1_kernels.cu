@@ -65,86 +65,80 @@ __device__ __forceinline__ void load_rgb(const uint8_t* __restrict__ row, int la
     }
 }
 
-constexpr uint32_t kNopRec = 0x100u;
-
 __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Records. k_model hands every range-coder bin to k_range / k_emit as (q, bit): q = sp - 1 where
+// sp = bit ? state : 256 - state is the 8-bit probability of the coded value (1..255), bit the coded value. q = 255
+// (sp = 256, bit 0) leaves the coder untouched; it pads every plane-row segment to whole 128-record blocks. Inside
+// k_model a record is the 16-bit value q | bit << 8 = 255 + (bit ? state : -state); in global memory the q bytes and the
+// bits (one bit-plane, record r = bit r & 7 of byte r >> 3) are separate arrays.
+constexpr uint32_t kNopRec = 0x00FFu;
+constexpr uint32_t kPoison = 0xFFFEu;
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_model
 //
 // One CTA per (frame, slice, plane-set) and band. Shared memory (dynamic):
-//   states  nctx*sstride B   adaptive state of every (context, slot) of this plane-set
+//   states  nctx*sstride B   adaptive state of every (context, slot) of this plane-set (32 B per context, 28 for 8-bit streams)
 //   ring    3 rows x planes x wmax int32   RCT'd samples of rows y, y-1, y-2
-//   val/off/ctx per sample of the plane-row being coded: folded residual (after the context-sign flip), first record of the
-//           sample inside the row, context index (>= 0)
-//   cnt8    per-context occurrence counter inside the current plane-row (touched only by the warp owning the context)
-//   tmp8    per-sample scratch byte: position inside its chunk-class group, later the round of the sample
-//   plist   samples of the row partitioned by owner warp (ctx mod 16), each part in x order
-//   ccnt    [chunk][class] counts -> exclusive prefix over chunks; ctot/coff the same for record counts
-//   rlist   kRounds lists of samples: round r = samples whose context occurred r times earlier in the row
-//   stage   the row's records, copied out coalesced at the end of the row
-constexpr int kRounds = 2;
-constexpr int kMaxChunks = 64;            // wmax <= 2048
-constexpr int kSlutRow = 36;              // slot of bin b of a symbol with exponent e: slut[e * kSlutRow + b], e <= 16, b <= 34
-constexpr int kSlutBytes = 17 * kSlutRow + 12;   // 624, keeps 16-byte alignment
+//   qtab    5 x 256 int16    quantisation tables
+//   t1      one_state, indexed by q: either replicated per bank ([64][32] words: lane l reads word (q >> 2) * 32 + l, no
+//           bank conflicts whatever the 32 lanes look up) or a plain 256-byte table when shared memory is short
+//   first   first-occurrence table: which sample of the plane-row is the first (in bitstream order) to use a context
+//   val/ctx/off/lflag per sample of the plane-row being coded: folded residual (after the context-sign flip), context,
+//           first record of the sample relative to its 32-sample chunk, leftover flag
+//   ctot    records per 32-sample chunk
+//   stage   the records of the plane-row (segment), 16 bit each, split into q bytes + bit-plane on the way out
+//
+// Per plane-row: S1 all samples in parallel: neighbours, context, residual, bin count, claim of the context ->
+// S2a every sample that is the FIRST user of its context in this row (all of them on grainy content): one lane per sample,
+// the 32 state bytes of the context in registers, all bins of the symbol -> S2b the other samples, in x order, by the warp
+// that owns the context class, one lane per slot -> S3 records to global memory.
 struct ModelSmem {
-    uint8_t* states; int32_t* ring; int32_t* val; uint32_t* off; uint16_t* ctx; uint8_t* cnt8; uint8_t* tmp8; uint16_t* plist;
-    uint16_t* ccnt; uint32_t* ctot; uint16_t* clstot; uint16_t* cstart; uint16_t* rlist; uint32_t* rfill; uint32_t* misc;
-    uint16_t* stage; int16_t* qtab; uint8_t* trans; uint8_t* slut; uint32_t* t2;
+    uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b; uint16_t* first;
+    int32_t* val; uint16_t* ctx; uint16_t* off; uint8_t* lflag; uint32_t* ctot; uint32_t* misc; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-__host__ __device__ inline int rlist_entries(int wmax) {  // NOLINT
-    int n = 0;
-    for (int r = 0; r < kRounds; r++) n += wmax / (r + 1) + 1;
-    return n;
-}
-// bytes of everything except the record staging area
-size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes) {
+constexpr int kMaxChunks = 64;            // wmax <= 2048
+
+// bytes of everything except the record staging area. first_n < 0: t1 not replicated, |first_n| entries.
+size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int first_n) {
+    const bool rep = first_n > 0;
+    const int fn = first_n > 0 ? first_n : -first_n;
     size_t n = align16((size_t)nctx * sstride);
     n += align16((size_t)3 * planes * wmax * 4);
-    n += align16((size_t)wmax * 4) * 2;          // val, off
-    n += align16((size_t)wmax * 2) * 2;          // ctx, plist
-    n += align16((size_t)nctx);                  // cnt8
-    n += align16((size_t)wmax);                  // tmp8
-    n += kMaxChunks * kModelWarps * 2 + kMaxChunks * 4 + 32 * 2 + 32 * 2;   // ccnt, ctot, clstot, cstart
-    n += align16((size_t)rlist_entries(wmax) * 2);
-    n += 16 * 4 + 16 * 4;                        // rfill, misc
-    n += 5 * 256 * 2 + 512 + kSlutBytes + 512 * 4;
+    n += 5 * 256 * 2;
+    n += rep ? 64 * 32 * 4 : 256;
+    n += align16((size_t)fn * 2);
+    n += align16((size_t)wmax * 4);          // val
+    n += align16((size_t)wmax * 2) * 2;      // ctx, off
+    n += align16((size_t)wmax);              // lflag
+    n += kMaxChunks * 4 + 16 * 4;            // ctot, misc
     return n;
 }
-size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int stage_cap) {
-    return model_smem_fixed(nctx, sstride, wmax, planes) + align16((size_t)stage_cap * 2);
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int first_n, int stage_cap) {
+    return model_smem_fixed(nctx, sstride, wmax, planes, first_n) + align16((size_t)stage_cap * 2);
 }
 
-__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes) {
+__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes, int first_n) {
+    const bool rep = first_n > 0;
+    const int fn = first_n > 0 ? first_n : -first_n;
     ModelSmem m;
     m.states = base; base += align16((size_t)nctx * sstride);
     m.ring = reinterpret_cast<int32_t*>(base); base += align16((size_t)3 * planes * wmax * 4);
-    m.val = reinterpret_cast<int32_t*>(base); base += align16((size_t)wmax * 4);
-    m.off = reinterpret_cast<uint32_t*>(base); base += align16((size_t)wmax * 4);
-    m.ctx = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
-    m.plist = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
-    m.cnt8 = base; base += align16((size_t)nctx);
-    m.tmp8 = base; base += align16((size_t)wmax);
-    m.ccnt = reinterpret_cast<uint16_t*>(base); base += kMaxChunks * kModelWarps * 2;
-    m.ctot = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * 4;
-    m.clstot = reinterpret_cast<uint16_t*>(base); base += 32 * 2;
-    m.cstart = reinterpret_cast<uint16_t*>(base); base += 32 * 2;
-    m.rlist = reinterpret_cast<uint16_t*>(base); base += align16((size_t)rlist_entries(wmax) * 2);
-    m.rfill = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
-    m.misc = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
     m.qtab = reinterpret_cast<int16_t*>(base); base += 5 * 256 * 2;
-    m.trans = base; base += 512;
-    m.slut = base; base += kSlutBytes;
-    m.t2 = reinterpret_cast<uint32_t*>(base); base += 512 * 4;
+    m.t1w = reinterpret_cast<uint32_t*>(base); m.t1b = base; base += rep ? 64 * 32 * 4 : 256;
+    m.first = reinterpret_cast<uint16_t*>(base); base += align16((size_t)fn * 2);
+    m.val = reinterpret_cast<int32_t*>(base); base += align16((size_t)wmax * 4);
+    m.ctx = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
+    m.off = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
+    m.lflag = base; base += align16((size_t)wmax);
+    m.ctot = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * 4;
+    m.misc = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
     m.stage = reinterpret_cast<uint16_t*>(base);
     return m;
 }
-
-// bin record handed from k_model to k_range / k_emit: sp | bit << 9 where sp = bit ? state : 256 - state is the 8-bit
-// probability of the coded value. kNopRec (sp = 256, bit 0) leaves the coder untouched; it pads every plane-row to whole
-// 128-byte blocks.
-__device__ __forceinline__ uint32_t make_rec(uint32_t st, uint32_t bit) { return (bit ? st : 256u - st) | (bit << 9); }
 
 constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
 
@@ -155,15 +149,41 @@ constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
 #define PHASE_MARK(k) do { } while (0)
 #endif
 
-// Byte offset of (context, slot) in the shared-memory state table. With 32 states per context every row starts on the
-// same 8 banks as the row four contexts further, so the word inside the row is XOR-swizzled with context bits 2..4:
-// lanes that touch the same slot of different contexts then spread over all 32 banks.
-__device__ __forceinline__ uint32_t state_off(uint32_t ctx, uint32_t slot, bool compact) {
-    return compact ? ctx * 27u + slot : ctx * 32u + (slot ^ (((ctx >> 2) & 7u) << 2));
+// position of a slot inside the state row of a context: 8-bit streams (folded residual of 9 bits, exponent <= 8) never
+// use slots 10, 20, 21, 30, 31, so their rows hold 27 states in 28 bytes
+template <bool kCompact>
+__host__ __device__ constexpr int cslot(int slot) { return kCompact ? slot - (slot > 10 ? 1 : 0) - (slot > 21 ? 2 : 0) : slot; }
+
+struct T1 {             // one_state lookup by q = sp - 1
+    const uint8_t* base;    // replicated: + lane * 4 already applied
+    bool rep;
+    __device__ __forceinline__ uint32_t operator()(uint32_t q) const {
+        if (rep) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(base + ((q & 0xFCu) << 5));
+            return (w >> ((q & 3u) * 8u)) & 255u;
+        }
+        return base[q];
+    }
+};
+
+// One bin on the register-resident state row: slot SLOT of the context whose states are in S. `used` lanes update the
+// state and write the record to *dst.
+template <bool kCompact, int SLOT>
+__device__ __forceinline__ void slot_step(uint32_t (&S)[8], bool used, bool bit, uint16_t* dst, const T1& t1) {
+    constexpr int ci = cslot<kCompact>(SLOT), wi = ci >> 2, sh = (ci & 3) * 8;
+    const uint32_t st = (S[wi] >> sh) & 255u;
+    const int s1 = bit ? 1 : -1;
+    const uint32_t rec = (uint32_t)((int)st * s1 + 255);            // q | bit << 8
+    const uint32_t n = t1(rec & 255u);                              // one_state[sp]
+    const uint32_t nx = (uint32_t)((int)n * s1 + (bit ? 0 : 256));  // bit ? one_state[st] : zero_state[st] = 256 - one_state[256 - st]
+    if (used) {
+        S[wi] = (S[wi] & ~(255u << sh)) | (nx << sh);
+        *dst = (uint16_t)rec;
+    }
 }
 
-__global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+template <bool kCompact>
+__device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t* smem_raw) {
     const int slice = blockIdx.x >> 1, ps = blockIdx.x & 1, frame = blockIdx.y;
     const SliceGeom g = A.geom[slice];
     const int r0 = band * A.band_rows;
@@ -172,15 +192,20 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     const int planes = ps ? 2 : 1;
     const int w = g.w, wmax = A.wmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
     constexpr int NW = kModelThreads / 32;
-    static_assert(NW == 16 || NW == 32, "context class = ctx & (NW - 1) = owner warp");
-    ModelSmem S = carve(smem_raw, A.nctx, A.sstride, wmax, planes);
+    constexpr int kRow = kCompact ? 28 : 32;                   // state bytes per context
+    constexpr int kWords = kCompact ? 7 : 8;
+    const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, planes, A.first_n);
+    const bool rep = A.first_n > 0;
+    const uint32_t first_n = (uint32_t)(A.first_n > 0 ? A.first_n : -A.first_n);
+    const uint32_t fmask = first_n >= (uint32_t)A.nctx ? 0xFFFFu : first_n - 1u;
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
-    const bool compact = A.sstride != 32;   // 8-bit streams never use slots 10, 20, 21, 30, 31 (e <= 8): 27 states per context
+    T1 t1;
+    t1.rep = rep;
+    t1.base = rep ? S.t1b + lane * 4 : S.t1b;
 
     const size_t fs = (size_t)frame * A.nslices + slice;
-    const int state_bytes = (int)align16((size_t)A.nctx * A.sstride);
+    const int state_bytes = (int)align16((size_t)A.nctx * kRow);
     uint8_t* save = A.state_save + (fs * 2 + ps) * (size_t)state_bytes;
     {   // context states: 128 at the start of every frame (intra-only), else carried from the previous band
         const int n16 = state_bytes >> 4;
@@ -193,21 +218,12 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
             for (int i = tid; i < n16; i += kModelThreads) d[i] = s[i];
         }
         for (int i = tid; i < 5 * 256; i += kModelThreads) S.qtab[i] = A.qtab[i];
-        for (int i = tid; i < 512; i += kModelThreads) S.trans[i] = A.trans[i];
-        for (int i = tid; i < (int)align16((size_t)A.nctx); i += kModelThreads) S.cnt8[i] = 0;
-        // t2[bit << 8 | state] = next state | record << 16: one lookup per bin gives the transition and the coder record
-        for (int i = tid; i < 512; i += kModelThreads) {
-            const uint32_t st = i & 255, bit = i >> 8;
-            S.t2[i] = (uint32_t)A.trans[i] | (make_rec(st, bit) << 16);
+        if (rep) {
+            for (int i = tid; i < 64 * 32; i += kModelThreads) S.t1w[i] = reinterpret_cast<const uint32_t*>(A.t1q)[i >> 5];
+        } else {
+            for (int i = tid; i < 256; i += kModelThreads) S.t1b[i] = A.t1q[i];
         }
-        // slot of bin b of a symbol with exponent e (rangecoder::s, FFV1_RangeCoder.cpp:135-171): zero flag (slot 0), unary
-        // exponent (1..10), mantissa from the top bit down (22..31), sign (11..21)
-        for (int i = tid; i < 17 * kSlutRow; i += kModelThreads) {
-            const int e = i / kSlutRow, b = i % kSlutRow;
-            int slot = b <= e + 1 ? min(b, 10) : (b <= 2 * e + 1 ? 22 + min(2 * e + 1 - b, 9) : 11 + min(e, 10));
-            if (compact) slot = slot - (slot > 10) - 2 * (slot > 21);
-            S.slut[i] = (uint8_t)slot;
-        }
+        for (int i = tid; i < wmax; i += kModelThreads) S.lflag[i] = 0;
     }
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
@@ -239,37 +255,36 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
     load_row(r0 - 1);
     load_row(r0);
 
-    uint16_t* bins = (ps ? A.binsC : A.binsY) + fs * (ps ? A.capC : A.capY);
-    uint32_t pos = 0;                       // records emitted so far in this band (CTA-uniform; segments start on multiples of 64)
-    uint32_t seg_extra = 0;                 // records already in the current segment (slice header ahead of the first Y row)
+    const size_t cap = ps ? A.capC : A.capY;
+    uint8_t* gq = (ps ? A.qC : A.qY) + fs * cap;
+    uint8_t* gb = (ps ? A.bC : A.bY) + fs * (cap >> 3);
+    uint32_t pos = 0;                       // records emitted so far in this band (CTA-uniform, multiple of 128)
+    uint32_t seg_extra = 0;                 // records already staged ahead of the next plane-row (the slice header)
     if (band == 0 && ps == 0) {
         const int nh = A.hdr_cnt[slice];
-        for (int i = tid; i < nh; i += kModelThreads) bins[i] = A.hdr_bins[(size_t)slice * kMaxHeaderBins + i];
-        pos = seg_extra = (uint32_t)nh;
+        for (int i = tid; i < nh; i += kModelThreads) S.stage[i] = A.hdr_bins[(size_t)slice * kMaxHeaderBins + i];
+        seg_extra = (uint32_t)nh;
     }
     __syncthreads();
 
     const int nchunk = (w + 31) >> 5;
-    const int KC = (nchunk + NW - 1) / NW;  // 32-sample chunks per warp
+    const int KC = (nchunk + NW - 1) / NW;  // 32-sample chunks per warp: chunk c belongs to warp c % NW
     const int sbits = A.sbits;
-    uint32_t* rl_off = S.misc + 4;           // first entry of round r in rlist
-    if (tid == 0) {
-        uint32_t o = 0;
-        for (int r = 0; r < kRounds; r++) { rl_off[r] = o; o += (uint32_t)(wmax / (r + 1) + 1); }
-    }
-    // lane -> slot class of the symbol binarisation for the slot-per-lane path (rangecoder::s, FFV1_RangeCoder.cpp:135-171):
+    // slot-per-lane path: lane -> slot class of the symbol binarisation (rangecoder::s, FFV1_RangeCoder.cpp:135-171):
     //   lane 0 zero flag | 1..10 exponent i = lane-1 (slot 10 also takes i > 9) | 11..21 sign for e = lane-11 |
     //   22..31 mantissa bit i = lane-22 (slot 31 also takes i > 9)
     const bool isB = lane >= 1 && lane <= 10, isD = lane >= 11 && lane <= 21;
     const int li = isB ? lane - 1 : isD ? lane - 11 : lane - 22;
-    const int lslot = compact ? lane - (lane > 10) - 2 * (lane > 21) : lane;
+    const bool lane_has_slot = !kCompact || !(lane == 10 || lane == 20 || lane == 21 || lane >= 30);
+    const int lslot = cslot<kCompact>(lane);
     unsigned long long bins_total = 0;
 #ifdef B200_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
 
     for (int y = r0; y < r1; y++) {
-        // software prefetch of the next payload row into registers; it lands in the ring after this row is coded
+        // software prefetch of the next payload row into registers; it lands in the ring once the last plane of this
+        // row has read its neighbours
         int nx0[kMaxPixPerThread], nx1[kMaxPixPerThread];
         const bool have_next = y + 1 < r1;
         if (have_next) {
@@ -283,15 +298,13 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
             const int32_t* cur = S.ring + ((size_t)((y + 3) % 3) * planes + pl) * wmax;
             const int32_t* prv = S.ring + ((size_t)((y + 2) % 3) * planes + pl) * wmax;
             const int32_t* pp2 = S.ring + ((size_t)((y + 1) % 3) * planes + pl) * wmax;
-            uint16_t* out = bins + pos;
-            if (tid <= kRounds) S.rfill[tid] = 0;
-            // ---- phase A (K2): prediction, context, fold, records per sample; per-chunk record totals and per-chunk counts of
-            // every context class (class = ctx & 15 = owner warp)
+            // ---- S1 (K2): prediction, context, fold, records per sample; claim of the context
             for (int k = 0; k < KC; k++) {
-                const int c = warp * KC + k;
+                const int c = k * NW + warp;
+                if (c >= nchunk) break;
                 const int x = c * 32 + lane;
                 const bool valid = x < w;
-                uint32_t nb = 0, cls = 32 + lane;
+                uint32_t nb = 0;
                 if (valid) {
                     const int T = prv[x];
                     const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
@@ -308,213 +321,198 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                     d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
                     S.val[x] = d;
                     S.ctx[x] = (uint16_t)ctx;
+                    S.first[(uint32_t)ctx & fmask] = (uint16_t)x;            // some user of the context wins; settled below
                     nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
-                    cls = (uint32_t)ctx & (uint32_t)(NW - 1);
                 }
                 uint32_t incl = nb;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const uint32_t m = __match_any_sync(0xffffffffu, cls);
-                if (c < kMaxChunks) {
-                    if (lane < NW) S.ccnt[c * NW + lane] = 0;
-                    if (lane == 31) S.ctot[c] = incl;
-                }
-                __syncwarp();
-                if (valid) {
-                    S.off[x] = incl - nb;                                      // chunk-relative for now
-                    const uint32_t intra = __popc(m & lt);
-                    S.tmp8[x] = (uint8_t)intra;
-                    if (intra == 0) S.ccnt[c * NW + cls] = (uint16_t)__popc(m);
-                }
+                if (valid) S.off[x] = (uint16_t)(incl - nb);
+                if (lane == 31) S.ctot[c] = incl;
             }
             __syncthreads();
             PHASE_MARK(0);
-            // ---- phase B1: exclusive prefix over chunks of the class counts (warp q: class q) and of the record totals (warp 0)
+            // the next payload row may now replace row y-2 (nobody reads it any more)
+            if (have_next && pl == planes - 1) {
+                int32_t* dst = S.ring + (size_t)((y + 4) % 3) * planes * wmax;
+#pragma unroll
+                for (int k = 0; k < kMaxPixPerThread; k++) {
+                    const int x = tid + k * kModelThreads;
+                    if (x < w) { dst[x] = nx0[k]; if (ps) dst[wmax + x] = nx1[k]; }
+                }
+            }
+            // ---- S2p: a sample that comes before the recorded winner of its table entry poisons the entry: then every
+            // sample of the entry takes the ordered path (S2b). Entries whose winner is the first user stay as they are.
+            for (int k = 0; k < KC; k++) {
+                const int c = k * NW + warp;
+                if (c >= nchunk) break;
+                const int x = c * 32 + lane;
+                if (x < w) {
+                    const uint32_t h = (uint32_t)S.ctx[x] & fmask;
+                    if ((uint32_t)S.first[h] > (uint32_t)x) S.first[h] = (uint16_t)kPoison;
+                }
+            }
+            // exclusive prefix of the chunk totals, every warp for itself: lane l holds chunks l and l + 32
+            uint32_t ex0, ex1, total;
             {
-                const int q = warp;
-                const int c0 = lane, c1 = lane + 32;
-                uint32_t v0 = c0 < nchunk ? S.ccnt[c0 * NW + q] : 0u, v1 = c1 < nchunk ? S.ccnt[c1 * NW + q] : 0u;
-                uint32_t i0 = v0, i1 = v1;
+                const uint32_t t0 = lane < nchunk ? S.ctot[lane] : 0u, t1v = lane + 32 < nchunk ? S.ctot[lane + 32] : 0u;
+                uint32_t i0 = t0, i1 = t1v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-                    if (lane >= o) { i0 += t0; i1 += t1; }
+                    const uint32_t a0 = __shfl_up_sync(0xffffffffu, i0, o), a1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) { i0 += a0; i1 += a1; }
                 }
-                const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-                if (c0 < nchunk) S.ccnt[c0 * NW + q] = (uint16_t)(i0 - v0);
-                if (c1 < nchunk) S.ccnt[c1 * NW + q] = (uint16_t)(tot0 + i1 - v1);
-                if (lane == 0) S.clstot[q] = (uint16_t)(tot0 + tot1);
-                if (warp == 0) {
-                    uint32_t a0 = c0 < nchunk ? S.ctot[c0] : 0u, a1 = c1 < nchunk ? S.ctot[c1] : 0u;
-                    uint32_t j0 = a0, j1 = a1;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        uint32_t t0 = __shfl_up_sync(0xffffffffu, j0, o), t1 = __shfl_up_sync(0xffffffffu, j1, o);
-                        if (lane >= o) { j0 += t0; j1 += t1; }
-                    }
-                    const uint32_t s0 = __shfl_sync(0xffffffffu, j0, 31), s1 = __shfl_sync(0xffffffffu, j1, 31);
-                    if (c0 < nchunk) S.ctot[c0] = j0 - a0;
-                    if (c1 < nchunk) S.ctot[c1] = s0 + j1 - a1;
-                    if (lane == 0) S.misc[0] = s0 + s1;                        // records of this plane-row
+                const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
+                ex0 = i0 - t0;
+                ex1 = tot0 + i1 - t1v;
+                total = tot0 + __shfl_sync(0xffffffffu, i1, 31);
+            }
+            auto chunk_base = [&](int c) -> uint32_t {     // c warp-uniform; c == nchunk gives the total
+                if (c >= nchunk) return total;
+                return c < 32 ? __shfl_sync(0xffffffffu, ex0, c) : __shfl_sync(0xffffffffu, ex1, c - 32);
+            };
+            // column segments: chunks [sc[s], sc[s+1]) whose records fit the stage together
+            int sc[kMaxSeg + 1];
+            int nsg = 0;
+            sc[0] = 0;
+            if (seg_extra + total <= stage_cap) { sc[1] = nchunk; nsg = 1; }
+            else {
+                int start = 0;
+                while (start < nchunk && nsg < kMaxSeg) {
+                    const uint32_t limit = chunk_base(start) + stage_cap - (start == 0 ? seg_extra : 0u);
+                    // inclusive prefix of chunk l / l + 32 beyond the limit?
+                    const uint32_t in0 = ex0 + (lane < nchunk ? S.ctot[lane] : 0u), in1 = ex1 + (lane + 32 < nchunk ? S.ctot[lane + 32] : 0u);
+                    const uint32_t f0 = __ballot_sync(0xffffffffu, lane < nchunk && in0 > limit);
+                    const uint32_t f1 = __ballot_sync(0xffffffffu, lane + 32 < nchunk && in1 > limit);
+                    unsigned long long F = ((unsigned long long)f1 << 32) | f0;
+                    F &= ~((1ull << start) - 1ull);
+                    int end = F ? __ffsll((long long)F) - 1 : nchunk;
+                    if (end <= start) end = start + 1;             // cannot happen: one chunk always fits (checked at open)
+                    sc[++nsg] = end;
+                    start = end;
                 }
+                if (start < nchunk) { if (tid == 0) atomicOr(A.flags, 4u); sc[nsg] = nchunk; }
             }
             __syncthreads();
             PHASE_MARK(1);
-            // ---- phase B2: final record offsets; samples partitioned by owner warp, x order kept
-            const uint32_t total = S.misc[0];
-            {
-                uint32_t ct = lane < NW ? S.clstot[lane] : 0u, ci = ct;
-#pragma unroll
-                for (int o = 1; o < NW; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ci, o); if (lane >= o) ci += t; }
-                const uint32_t cst = ci - ct;                                   // lane q < 16: first plist entry of class q
-                if (warp == 0 && lane < NW) S.cstart[lane] = (uint16_t)cst;
+
+            const uint32_t rc_base = ((uint32_t)(fs * A.band_rows + (y - r0)) * 3u + (uint32_t)(ps ? 1 + pl : 0)) * (uint32_t)A.nseg;
+            for (int s = 0; s < nsg; s++) {
+                const int c0 = sc[s], c1 = sc[s + 1];
+                const uint32_t extra = s == 0 ? seg_extra : 0u;
+                const uint32_t segbase = chunk_base(c0);
+                const uint32_t seg_total = extra + chunk_base(c1) - segbase;
+                // ---- S2a (K3): first users of their context, one lane per sample, state row in registers
                 for (int k = 0; k < KC; k++) {
-                    const int c = warp * KC + k;
+                    const int c = k * NW + warp;
+                    if (c >= nchunk) break;
+                    if (c < c0 || c >= c1) continue;
                     const int x = c * 32 + lane;
                     const bool valid = x < w;
-                    const uint32_t cls = valid ? (S.ctx[x] & (uint32_t)(NW - 1)) : 0u;
-                    const uint32_t base = __shfl_sync(0xffffffffu, cst, cls);
+                    int v = 0;
+                    uint32_t cx = 0, o = 0;
+                    bool win = false;
+                    const uint32_t cb = chunk_base(c);
                     if (valid) {
-                        S.off[x] += S.ctot[c];
-                        S.plist[base + S.ccnt[c * NW + cls] + S.tmp8[x]] = (uint16_t)x;
+                        v = S.val[x];
+                        cx = S.ctx[x];
+                        o = extra + cb - segbase + S.off[x];
+                        win = (uint32_t)S.first[cx & fmask] == (uint32_t)x;
+                        if (!win) S.lflag[x] = (uint8_t)(1u + (cx & (uint32_t)(NW - 1)));
                     }
-                }
-            }
-            __syncthreads();
-            PHASE_MARK(2);
-            // ---- phase C: warp q ranks the samples of its context class: round = occurrences of the context earlier in the row
-            {
-                const uint32_t n = S.clstot[warp], base = S.cstart[warp];
-                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-                    const bool valid = i0 + lane < n;
-                    const uint32_t x = valid ? S.plist[base + i0 + lane] : 0u;
-                    const uint32_t cx = valid ? S.ctx[x] : (0x10000u | lane);
-                    const uint32_t m = __match_any_sync(0xffffffffu, cx);
-                    const uint32_t b0 = valid ? S.cnt8[cx] : 0u;
-                    const uint32_t r = b0 + __popc(m & lt);
-                    __syncwarp();
-                    if (valid && (m >> lane) == 1u) S.cnt8[cx] = (uint8_t)min(255u, b0 + __popc(m));   // highest lane of the group
-                    __syncwarp();
-                    const uint32_t rr = valid ? min(r, (uint32_t)kRounds) : (32u + lane);
-                    const uint32_t m2 = __match_any_sync(0xffffffffu, rr);
-                    const int lead = __ffs(m2) - 1;
-                    uint32_t bs = 0;
-                    if (valid && lead == lane) bs = atomicAdd(&S.rfill[rr], (uint32_t)__popc(m2));
-                    bs = __shfl_sync(0xffffffffu, bs, lead);
-                    if (valid) {
-                        S.tmp8[x] = (uint8_t)rr;
-                        if (rr < (uint32_t)kRounds) S.rlist[rl_off[rr] + bs + __popc(m2 & lt)] = (uint16_t)x;
-                    }
-                }
-                __syncwarp();
-                for (uint32_t i0 = lane; i0 < n; i0 += 32) S.cnt8[S.ctx[S.plist[base + i0]]] = 0;
-            }
-            __syncthreads();
-            PHASE_MARK(3);
-            // ---- phase D (K3): two samples per lane (independent chains, interleaved), all their bins; round by round (contexts
-            // inside a round are distinct, so the order inside a round is free)
-            for (int r = 0; r < kRounds; r++) {
-                const uint32_t nr = S.rfill[r];
-                if (nr == 0) break;
-                for (uint32_t i0 = (uint32_t)warp * 64; i0 < nr; i0 += kModelThreads * 2) {
-                    uint32_t nb[2] = {0, 0}, o[2] = {0, 0}, lo[2] = {0, 0}, hi[2] = {0, 0}, sbase[2] = {0, 0}, swz[2] = {0, 0};
-                    uint32_t lw[2][9];
+                    const bool nz = v != 0;
+                    const uint32_t a = (uint32_t)abs(v);
+                    const int e = nz ? 31 - __clz(a) : -1;
+                    const int emax = __reduce_max_sync(0xffffffffu, win ? e : -1);
+                    if (!__any_sync(0xffffffffu, win)) continue;
+                    const int emin = __reduce_min_sync(0xffffffffu, (win && nz) ? e : 99);
+                    const bool neg = v < 0;
+                    const bool wnz = win && nz;
+                    uint16_t* pL = S.stage + o;
+                    uint16_t* pR = pL + (2 * e + 2);
+                    uint32_t R[8];
+                    uint8_t* row = S.states + (size_t)cx * kRow;
+                    if (win) {
+                        if (!kCompact) {
+                            const uint4 q0 = reinterpret_cast<const uint4*>(row)[0], q1 = reinterpret_cast<const uint4*>(row)[1];
+                            R[0] = q0.x; R[1] = q0.y; R[2] = q0.z; R[3] = q0.w; R[4] = q1.x; R[5] = q1.y; R[6] = q1.z; R[7] = q1.w;
+                        } else {
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const uint32_t j = i0 + q * 32 + lane;
-                        uint32_t e = 0;
-                        if (j < nr) {
-                            const uint32_t x = S.rlist[rl_off[r] + j];
-                            const int v = S.val[x];
-                            const uint32_t cxd = S.ctx[x];
-                            o[q] = S.off[x];
-                            sbase[q] = compact ? cxd * 27u : cxd * 32u;
-                            swz[q] = compact ? 0u : ((cxd >> 2) & 7u) << 2;
-                            const uint32_t a = (uint32_t)abs(v);
-                            if (v == 0) { nb[q] = 1; lo[q] = 1; }
-                            else {
-                                e = 31 - __clz(a);
-                                nb[q] = 2 * e + 3;
-                                const uint32_t mant = e ? (__brev(a & ((1u << e) - 1u)) >> (32 - e)) : 0u;   // bit i of a -> bit e-1-i
-                                const uint64_t bw = (uint64_t)(((1u << e) - 1u) << 1) | ((uint64_t)mant << (e + 2)) | ((uint64_t)(v < 0) << (2 * e + 2));
-                                lo[q] = (uint32_t)bw; hi[q] = (uint32_t)(bw >> 32);
-                            }
-                        }
-                        const uint32_t* lrow = reinterpret_cast<const uint32_t*>(S.slut + e * kSlutRow);
-#pragma unroll
-                        for (int k = 0; k < 9; k++) lw[q][k] = lrow[k];
-                    }
-                    const uint32_t nbmax = __reduce_max_sync(0xffffffffu, max(nb[0], nb[1]));
-                    const bool fits = __all_sync(0xffffffffu, o[0] + nb[0] <= stage_cap && o[1] + nb[1] <= stage_cap);
-                    uint8_t* sb0 = S.states + sbase[0];
-                    uint8_t* sb1 = S.states + sbase[1];
-                    if (fits) {
-                        uint16_t* so0 = S.stage + o[0];
-                        uint16_t* so1 = S.stage + o[1];
-#pragma unroll
-                        for (uint32_t b = 0; b < 35; b++) {
-                            if (b >= nbmax) break;
-                            const bool p0 = b < nb[0], p1 = b < nb[1];
-                            uint8_t* s0 = sb0 + (((lw[0][b >> 2] >> ((b & 3) * 8)) & 255u) ^ swz[0]);
-                            uint8_t* s1 = sb1 + (((lw[1][b >> 2] >> ((b & 3) * 8)) & 255u) ^ swz[1]);
-                            uint32_t st0 = 0, st1 = 0;
-                            if (p0) st0 = *s0;
-                            if (p1) st1 = *s1;
-                            const uint32_t bit0 = b < 32 ? (lo[0] >> b) & 1u : (hi[0] >> (b - 32)) & 1u;
-                            const uint32_t bit1 = b < 32 ? (lo[1] >> b) & 1u : (hi[1] >> (b - 32)) & 1u;
-                            const uint32_t t0 = S.t2[(bit0 << 8) | st0];
-                            const uint32_t t1 = S.t2[(bit1 << 8) | st1];
-                            if (p0) { *s0 = (uint8_t)t0; so0[b] = (uint16_t)(t0 >> 16); }
-                            if (p1) { *s1 = (uint8_t)t1; so1[b] = (uint16_t)(t1 >> 16); }
+                            for (int i = 0; i < kWords; i++) R[i] = reinterpret_cast<const uint32_t*>(row)[i];
+                            R[7] = 0;
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            uint8_t* sbq = q ? sb1 : sb0;
-                            for (uint32_t b = 0; b < nbmax; b++) {
-                                if (b < nb[q]) {
-                                    const uint32_t e = (nb[q] - 3) >> 1;
-                                    uint8_t* sp = sbq + ((nb[q] == 1 ? 0u : (uint32_t)S.slut[e * kSlutRow + b]) ^ swz[q]);
-                                    const uint32_t bit = b < 32 ? (lo[q] >> b) & 1u : (hi[q] >> (b - 32)) & 1u;
-                                    const uint32_t tt = S.t2[(bit << 8) | *sp];
-                                    *sp = (uint8_t)tt;
-                                    const uint32_t idx = o[q] + b;
-                                    if (idx < stage_cap) S.stage[idx] = (uint16_t)(tt >> 16); else out[idx] = (uint16_t)(tt >> 16);
-                                }
-                            }
+                        for (int i = 0; i < 8; i++) R[i] = 0x80808080u;
+                    }
+                    slot_step<kCompact, 0>(R, win, !nz, pL, t1);
+                    // exponent, unary: bins 1 + i, i = 0..e (1 while i < e)
+#define EXP_STEP(i) if ((i) <= emax) slot_step<kCompact, 1 + (i)>(R, wnz && (i) <= e, (i) < e, pL + 1 + (i), t1);
+                    EXP_STEP(0) EXP_STEP(1) EXP_STEP(2) EXP_STEP(3) EXP_STEP(4) EXP_STEP(5) EXP_STEP(6) EXP_STEP(7) EXP_STEP(8)
+#undef EXP_STEP
+                    if (!kCompact) {
+                        for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, wnz && i <= e, i < e, pL + 1 + i, t1);
+                    }
+                    // sign: bin 2e + 2, slot 11 + min(e, 10)
+#define SGN_STEP(j) if ((j) >= emin && (j) <= emax) slot_step<kCompact, 11 + (j)>(R, wnz && e == (j), neg, pR, t1);
+                    SGN_STEP(0) SGN_STEP(1) SGN_STEP(2) SGN_STEP(3) SGN_STEP(4) SGN_STEP(5) SGN_STEP(6) SGN_STEP(7) SGN_STEP(8)
+                    if (!kCompact) {
+                        SGN_STEP(9)
+                        if (emax >= 10) slot_step<kCompact, 21>(R, wnz && e >= 10, neg, pR, t1);
+                    }
+#undef SGN_STEP
+                    // mantissa, from the top bit down: bit i is bin 2e + 1 - i, slot 22 + min(i, 9)
+                    if (!kCompact) {
+                        for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, wnz && i < e, (a >> i) & 1u, pR - 1 - i, t1);
+                    }
+#define MAN_STEP(i) if ((i) < emax) slot_step<kCompact, 22 + (i)>(R, wnz && (i) < e, (a >> (i)) & 1u, pR - 1 - (i), t1);
+                    if (!kCompact) { MAN_STEP(8) }
+                    MAN_STEP(7) MAN_STEP(6) MAN_STEP(5) MAN_STEP(4) MAN_STEP(3) MAN_STEP(2) MAN_STEP(1) MAN_STEP(0)
+#undef MAN_STEP
+                    if (win) {
+                        if (!kCompact) {
+                            reinterpret_cast<uint4*>(row)[0] = make_uint4(R[0], R[1], R[2], R[3]);
+                            reinterpret_cast<uint4*>(row)[1] = make_uint4(R[4], R[5], R[6], R[7]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < kWords; i++) reinterpret_cast<uint32_t*>(row)[i] = R[i];
                         }
                     }
                 }
+                // no-op records up to the next whole block
+                const uint32_t padded = (seg_total + (uint32_t)kBlockRecs - 1u) & ~((uint32_t)kBlockRecs - 1u);
+                if ((uint32_t)tid < padded - seg_total) S.stage[seg_total + tid] = (uint16_t)kNopRec;
                 __syncthreads();
-            }
-            PHASE_MARK(4);
-            // ---- phase E: samples beyond kRounds occurrences of their context (flat areas): the owner warp walks them in x order,
-            // one sample per step, lane s = slot s of the context (slots are independent chains)
-            if (S.rfill[kRounds]) {
-                const uint32_t n = S.clstot[warp], base = S.cstart[warp];
-                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-                    const bool valid = i0 + lane < n;
-                    const uint32_t xl = valid ? S.plist[base + i0 + lane] : 0u;
-                    uint32_t todo = __ballot_sync(0xffffffffu, valid && S.tmp8[xl] == kRounds);
+                PHASE_MARK(2);
+                // ---- S2b: the other samples, in x order: warp q walks the samples of context class q (ctx mod NW), one sample
+                // per step, lane s = slot s of the context (slots are independent chains)
+                for (int c = c0; c < c1; c++) {
+                    const int xl = c * 32 + lane;
+                    const uint32_t fl = xl < w ? S.lflag[xl] : 0u;
+                    uint32_t todo = __ballot_sync(0xffffffffu, fl == (uint32_t)(warp + 1));
+                    if (!todo) continue;
+                    if (fl == (uint32_t)(warp + 1)) S.lflag[xl] = 0;
+                    const uint32_t cb = extra + chunk_base(c) - segbase;
                     while (todo) {
                         const int j = __ffs(todo) - 1;
                         todo &= todo - 1;
-                        const uint32_t x = __shfl_sync(0xffffffffu, xl, j);
+                        const int x = c * 32 + j;
                         const int v = S.val[x];                 // warp-uniform
-                        const uint32_t ob = S.off[x];
+                        const uint32_t ob = cb + S.off[x];
                         const uint32_t a = (uint32_t)abs(v);
                         const int e = 31 - __clz(a | 1);
-                        uint8_t* sp = S.states + state_off(S.ctx[x], (uint32_t)lslot, compact);
+                        uint8_t* sp = S.states + (size_t)S.ctx[x] * kRow + lslot;
                         if (e <= 8) {
                             const bool nz = v != 0;
-                            const bool has = lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e));
-                            const uint32_t bit = lane == 0 ? !nz : isB ? (uint32_t)(li < e) : isD ? (uint32_t)(v < 0) : ((a >> li) & 1u);
+                            const bool has = lane_has_slot && (lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e)));
+                            const bool bit = lane == 0 ? !nz : isB ? (li < e) : isD ? (v < 0) : (((a >> li) & 1u) != 0);
                             const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * e + 2 : 2 * e + 1 - li;
                             if (has) {
                                 const uint32_t st = *sp;
-                                const uint32_t rec = make_rec(st, bit);
-                                if (ob + idx < stage_cap) S.stage[ob + idx] = (uint16_t)rec; else out[ob + idx] = (uint16_t)rec;
-                                *sp = S.trans[(bit << 8) | st];
+                                const int s1 = bit ? 1 : -1;
+                                const uint32_t rec = (uint32_t)((int)st * s1 + 255);
+                                S.stage[ob + idx] = (uint16_t)rec;
+                                *sp = (uint8_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
                             }
                         } else {
                             int n2 = 0, i0b = 0, step = 0;     // n2 bins; bin k uses index i = i0b + k*step
@@ -528,14 +526,15 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                                 uint32_t st = *sp;
                                 for (int k = 0; k < n2; k++) {
                                     const int i = i0b + k * step;
-                                    uint32_t bit, idx;
-                                    if (lane == 0) { bit = 0; idx = 0; }
+                                    bool bit; uint32_t idx;
+                                    if (lane == 0) { bit = false; idx = 0; }
                                     else if (lane <= 10) { bit = i < e; idx = 1 + i; }
                                     else if (lane <= 21) { bit = v < 0; idx = 2 * e + 2; }
-                                    else { bit = (a >> i) & 1; idx = 2 * e + 1 - i; }
-                                    const uint32_t rec = make_rec(st, bit);
-                                    if (ob + idx < stage_cap) S.stage[ob + idx] = (uint16_t)rec; else out[ob + idx] = (uint16_t)rec;
-                                    st = S.trans[(bit << 8) | st];
+                                    else { bit = ((a >> i) & 1u) != 0; idx = 2 * e + 1 - i; }
+                                    const int s1 = bit ? 1 : -1;
+                                    const uint32_t rec = (uint32_t)((int)st * s1 + 255);
+                                    S.stage[ob + idx] = (uint16_t)rec;
+                                    st = (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
                                 }
                                 *sp = (uint8_t)st;
                             }
@@ -544,53 +543,62 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
                     }
                 }
                 __syncthreads();
-            }
-            PHASE_MARK(5);
-            // ---- phase F: staged records -> global, coalesced; pad the segment to a whole 128-byte block with no-op records
-            {
-                const uint32_t ns = min(total, stage_cap);
-                if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-                    const uint32_t nv = ns >> 3;
+                PHASE_MARK(3);
+                // ---- S3: staged records -> global: q bytes and bit-plane, whole blocks, coalesced
+                {
+                    const uint32_t ngrp = padded >> 4;          // groups of 16 records; a multiple of 8
+                    uint4* dq = reinterpret_cast<uint4*>(gq + pos);
+                    uint32_t* db = reinterpret_cast<uint32_t*>(gb + (pos >> 3));
                     const uint4* sv = reinterpret_cast<const uint4*>(S.stage);
-                    uint4* dv = reinterpret_cast<uint4*>(out);
-                    for (uint32_t i = tid; i < nv; i += kModelThreads) dv[i] = sv[i];
-                    for (uint32_t i = (nv << 3) + tid; i < ns; i += kModelThreads) out[i] = S.stage[i];
-                } else {
-                    for (uint32_t i = tid; i < ns; i += kModelThreads) out[i] = S.stage[i];
+                    for (uint32_t g0 = (uint32_t)warp * 32u; g0 < ngrp; g0 += kModelThreads) {
+                        const uint32_t gi = g0 + lane;
+                        const bool ok = gi < ngrp;
+                        uint32_t bits16 = 0;
+                        if (ok) {
+                            const uint4 a = sv[2 * gi], b = sv[2 * gi + 1];
+                            uint4 qv;
+                            qv.x = __byte_perm(a.x, a.y, 0x6420); qv.y = __byte_perm(a.z, a.w, 0x6420);
+                            qv.z = __byte_perm(b.x, b.y, 0x6420); qv.w = __byte_perm(b.z, b.w, 0x6420);
+                            dq[gi] = qv;
+                            const uint32_t h0 = __byte_perm(a.x, a.y, 0x7531), h1 = __byte_perm(a.z, a.w, 0x7531);
+                            const uint32_t h2 = __byte_perm(b.x, b.y, 0x7531), h3 = __byte_perm(b.z, b.w, 0x7531);
+                            bits16 = ((h0 * 0x01020408u) >> 24) | (((h1 * 0x01020408u) >> 24) << 4) |
+                                     (((h2 * 0x01020408u) >> 24) << 8) | (((h3 * 0x01020408u) >> 24) << 12);
+                        }
+                        const uint32_t other = __shfl_xor_sync(0xffffffffu, bits16, 1);
+                        if (ok && !(lane & 1)) db[gi >> 1] = bits16 | (other << 16);
+                    }
+                    if (tid == 0) A.rowcnt[rc_base + s] = seg_total;
+                    pos += padded;
+                    bins_total += seg_total - extra;
                 }
-                PHASE_MARK(7);
-                const uint32_t seg_len = seg_extra + total;
-                const uint32_t pad = ((seg_len + 63u) & ~63u) - seg_len;
-                if (tid < (int)pad) out[total + tid] = (uint16_t)kNopRec;
-                if (tid == 0) A.rowcnt[(fs * A.band_rows + (y - r0)) * 3 + (ps ? 1 + pl : 0)] = seg_len;
-                pos += total + pad;
-                seg_extra = 0;
-                bins_total += total;
+                if (s + 1 < nsg) __syncthreads();
+                PHASE_MARK(4);
             }
-            __syncthreads();
-            PHASE_MARK(6);
+            if (tid == 0) for (int s = nsg; s < A.nseg; s++) A.rowcnt[rc_base + s] = 0;
+            seg_extra = 0;
         }
-        if (have_next) {
-            int32_t* dst = S.ring + (size_t)((y + 4) % 3) * planes * wmax;
-#pragma unroll
-            for (int k = 0; k < kMaxPixPerThread; k++) {
-                const int x = tid + k * kModelThreads;
-                if (x < w) { dst[x] = nx0[k]; if (ps) dst[wmax + x] = nx1[k]; }
-            }
-            __syncthreads();
-        }
-        PHASE_MARK(7);
     }
 #ifdef B200_PHASE_TIMING
     if (tid == 0) for (int k = 0; k < 8; k++) atomicAdd(reinterpret_cast<unsigned long long*>(A.flags + 16) + k, (unsigned long long)ph[k]);
 #endif
     if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(A.flags + 2), bins_total);
+    __syncthreads();
     if (r1 < g.h) {   // carry the states to the next band
         const int n16 = state_bytes >> 4;
         const uint4* s = reinterpret_cast<const uint4*>(S.states);
         uint4* d = reinterpret_cast<uint4*>(save);
         for (int i = tid; i < n16; i += kModelThreads) d[i] = s[i];
     }
+}
+
+__global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    k_model_body<false>(A, band, smem_raw);
+}
+__global__ void __launch_bounds__(kModelThreads, 1) k_model_compact(const __grid_constant__ EncArgs A, int band) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    k_model_body<true>(A, band, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -601,21 +609,15 @@ __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constan
 // top byte of the 16-bit window leaves). Only `range` and the number of renormalisations form a serial recurrence.
 //
 //   k_range  one lane per (frame, slice): runs just that recurrence — range' = renorm((range * sp + c) >> 8) and the
-//            shift count — over the slice's records, ~9 instructions per bin, branch-free, records staged through
-//            shared memory with cp.async. Every 64 records (one 128-byte block) it leaves a checkpoint (range, bytes so far).
-//   k_emit   one thread per 64-record block, fully parallel: replays the block from its checkpoint with the complete
-//            coder step and adds the block's contribution into the slice's byte stream, held as big-endian 32-bit words,
-//            with atomic adds (neighbouring blocks overlap by the 16-bit window and by carries; addition commutes).
+//            shift count — over the slice's records, branch-free, records prefetched four 16-record groups ahead into
+//            registers (no shared memory: its CTAs run beside k_model's). Every 64 records it leaves a checkpoint
+//            (range, bytes so far).
+//   k_emit   one thread per 64 records, fully parallel: replays them from the checkpoint with the complete coder step and
+//            adds the contribution into the slice's byte stream, held as big-endian 32-bit words, with atomic adds
+//            (neighbouring pieces overlap by the 16-bit window and by carries; addition commutes).
 //
 // Slice header bins are ordinary records at the head of the Y stream (written by k_model), the terminator bin only moves
 // `range` (k_range), and the coder's final flush is a single +0xFF (k_range). CRC and footer: k_pack.
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // add v into big-endian word idx of the slice stream, propagating wrap-arounds towards the front
 __device__ __forceinline__ void stream_add(uint32_t* W, int64_t idx, uint32_t v) {
@@ -626,20 +628,41 @@ __device__ __forceinline__ void stream_add(uint32_t* W, int64_t idx, uint32_t v)
     }
 }
 
-__device__ __forceinline__ void range_step(uint32_t rec, uint32_t& range, uint32_t& cnt) {
-    const uint32_t sp = rec & 0x1FFu;
-    const uint32_t x = range * sp + ((rec & 0x200u) ? 0u : 255u);   // bit 0: range - ((range*state)>>8) == (range*(256-state)+255)>>8
+__device__ __forceinline__ void range_step(uint32_t sp, uint32_t c, uint32_t& range, uint32_t& cnt) {
+    const uint32_t x = range * sp + c;     // bit 0: range - ((range*state)>>8) == (range*(256-state)+255)>>8, so c = 255
     const bool sh = x < 0x10000u;
     range = sh ? (x & 0xFFFF00u) : (x >> 8);
     cnt += sh;
 }
 
-constexpr int kRingBlocks = 4;          // 128-byte blocks in flight per lane
-constexpr int kMaxBandRows = 64;
+constexpr int kCkptRecs = 64;
+constexpr int kRangeDepth = 4;          // 16-record groups in flight per lane
+
+// 0xFF when the most significant bit of byte `byte` of v is set, else 0 (prmt's sign-replication mode)
+template <int kByte>
+__device__ __forceinline__ uint32_t msb_mask(uint32_t v) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v), "r"(0u), "r"(0x4440u | 8u | (uint32_t)kByte));
+    return d;
+}
+template <int kByte>
+__device__ __forceinline__ uint32_t get_byte(uint32_t v) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v), "r"(0u), "r"(0x4440u | (uint32_t)kByte));
+    return d;
+}
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u16(const void* p) {
+    uint16_t v;
+    asm volatile("ld.global.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
 
 __global__ void __launch_bounds__(32) k_range(const __grid_constant__ EncArgs A, int band, int nframes) {
-    __shared__ uint4 s_ring[kRingBlocks][8][32];
-    __shared__ uint16_t s_cnt[kMaxBandRows * 3][32];                // blocks per segment (plane-row)
     const int lane = threadIdx.x;
     const int gid = blockIdx.x * 32 + lane;
     const bool in_range = gid < nframes * A.nslices;
@@ -648,85 +671,77 @@ __global__ void __launch_bounds__(32) k_range(const __grid_constant__ EncArgs A,
     const int r0 = band * A.band_rows;
     const bool valid = in_range && r0 < g.h;
     const int r1 = min(r0 + A.band_rows, g.h);
-    const int nseg = valid ? (r1 - r0) * 3 : 0;
+    const int nseg = A.nseg;
+    const int nt = valid ? (r1 - r0) * 3 * nseg : 0;           // segments in bitstream order: row, plane, column segment
     const size_t gsafe = in_range ? (size_t)gid : 0;
+    const uint32_t* rc = A.rowcnt + gsafe * A.band_rows * 3 * nseg;
 
-    uint32_t total = 0, usedY = 0, usedC = 0;                       // 64-record blocks this lane consumes in this band
-    if (valid) {
-        const uint32_t* rc = A.rowcnt + gsafe * A.band_rows * 3;
-        for (int s = 0; s < nseg; s++) {
-            const uint32_t c = (rc[s] + 63u) >> 6;
-            s_cnt[s][lane] = (uint16_t)c;
-            total += c;
-            if (s % 3 == 0) usedY += c; else usedC += c;
-        }
-    }
-    if (in_range) { A.used[gsafe * 2] = usedY; A.used[gsafe * 2 + 1] = usedC; }
-    uint32_t maxb = total;
+    uint32_t total = 0;                                         // 16-record groups this lane consumes in this band
+    for (int t = 0; t < nt; t++) total += ((rc[t] + 127u) >> 7) << 3;
+    uint32_t maxg = total;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, o));
+    for (int o = 16; o; o >>= 1) maxg = max(maxg, __shfl_xor_sync(0xffffffffu, maxg, o));
 
     uint32_t range = 0xFF00u, cnt = 0;
     if (valid && band > 0) { const CoderState s = A.cstate[gid]; range = s.range; cnt = s.pos; }
 
-    const uint4* pY = reinterpret_cast<const uint4*>(A.binsY + gsafe * A.capY);
-    const uint4* pC = reinterpret_cast<const uint4*>(A.binsC + gsafe * A.capC);
-    uint2* kY = A.ckptY + gsafe * (A.capY >> 6);
-    uint2* kC = A.ckptC + gsafe * (A.capC >> 6);
-    // two cursors over the lane's segments (Y row, Cb row, Cr row, Y row, ...): prefetch runs kRingBlocks-1 blocks ahead
-    int pf_seg = -1, pf_pl = 2, cs_seg = -1, cs_pl = 2;
-    uint32_t pf_rem = 0, cs_rem = 0;
-    auto next_src = [&]() -> const uint4* {
-        while (pf_rem == 0) {
-            if (++pf_seg >= nseg) return nullptr;
-            pf_pl = pf_pl == 2 ? 0 : pf_pl + 1;
-            pf_rem = s_cnt[pf_seg][lane];
+    const uint8_t* qY = A.qY + gsafe * A.capY;
+    const uint8_t* qC = A.qC + gsafe * A.capC;
+    const uint8_t* bY = A.bY + gsafe * (A.capY >> 3);
+    const uint8_t* bC = A.bC + gsafe * (A.capC >> 3);
+    uint2* kY = A.ckptY + gsafe * (A.capY / kCkptRecs);
+    uint2* kC = A.ckptC + gsafe * (A.capC / kCkptRecs);
+
+    // cursor over the lane's segments
+    int t = -1;
+    uint32_t rem = 0, giY = 0, giC = 0, isC = 0;
+    uint32_t cnt_pref = nt > 0 ? rc[0] : 0u;
+    uint4 Q[kRangeDepth];
+    uint32_t Bw[kRangeDepth], M[kRangeDepth];                   // bits of the group; M: bit 31 checkpoint due, bit 30 C stream, low bits group index
+    auto load_next = [&](int u) {
+        while (rem == 0 && t + 1 < nt) {
+            t++;
+            const uint32_t c = cnt_pref;
+            cnt_pref = t + 1 < nt ? rc[t + 1] : 0u;
+            rem = ((c + 127u) >> 7) << 3;
+            isC = ((t / nseg) % 3) != 0;
         }
-        pf_rem--;
-        const uint4* p = pf_pl == 0 ? pY : pC;
-        if (pf_pl == 0) pY += 8; else pC += 8;
-        return p;
-    };
-    auto next_ckpt = [&]() -> uint2* {
-        while (cs_rem == 0) {
-            if (++cs_seg >= nseg) return nullptr;
-            cs_pl = cs_pl == 2 ? 0 : cs_pl + 1;
-            cs_rem = s_cnt[cs_seg][lane];
+        if (rem == 0) {
+            Q[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            Bw[u] = 0; M[u] = 0;
+            return;
         }
-        cs_rem--;
-        return cs_pl == 0 ? kY++ : kC++;
+        rem--;
+        const uint32_t gi = isC ? giC : giY;
+        Q[u] = ldg_stream16((isC ? qC : qY) + (size_t)gi * 16);
+        Bw[u] = ldg_stream_u16((isC ? bC : bY) + (size_t)gi * 2);
+        M[u] = gi | (isC << 30) | ((gi & 3u) == 0 ? 0x80000000u : 0u);
+        if (isC) giC++; else giY++;
     };
-    auto prefetch = [&](int slot) {
-        const uint4* p = next_src();
-        if (p) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) cp_async16(&s_ring[slot][u][lane], p + u);
-        }
-        cp_async_commit();
-    };
-    for (int i = 0; i < kRingBlocks - 1; i++) prefetch(i);
-    const uint32_t nop2 = kNopRec | (kNopRec << 16);
-    for (uint32_t bi = 0; bi < maxb; bi++) {
-        prefetch((bi + kRingBlocks - 1) % kRingBlocks);
-        cp_async_wait<kRingBlocks - 1>();
-        const bool live = bi < total;
-        uint2* ck = next_ckpt();
-        if (ck) *ck = make_uint2(range, cnt);
-        const int slot = bi % kRingBlocks;
+    for (int u = 0; u < kRangeDepth; u++) load_next(u);
+    for (uint32_t gi0 = 0; gi0 < maxg; gi0 += kRangeDepth) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            uint4 q = s_ring[slot][u][lane];
-            if (!live) q = make_uint4(nop2, nop2, nop2, nop2);
-            range_step(q.x & 0xFFFFu, range, cnt); range_step(q.x >> 16, range, cnt);
-            range_step(q.y & 0xFFFFu, range, cnt); range_step(q.y >> 16, range, cnt);
-            range_step(q.z & 0xFFFFu, range, cnt); range_step(q.z >> 16, range, cnt);
-            range_step(q.w & 0xFFFFu, range, cnt); range_step(q.w >> 16, range, cnt);
+        for (int u = 0; u < kRangeDepth; u++) {
+            const uint4 q = Q[u];
+            const uint32_t nbits = ~Bw[u];
+            const uint32_t m = M[u];
+            load_next(u);
+            if (m & 0x80000000u) {
+                uint2* ck = ((m >> 30) & 1u ? kC : kY) + ((m & 0x3FFFFFFFu) >> 2);
+                *ck = make_uint2(range, cnt);
+            }
+            const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
+#define RSTEP(k) range_step(get_byte<((k) & 3)>(ww[(k) >> 2]) + 1u, msb_mask<((k) >> 3)>(nbits << (7 - ((k) & 7))), range, cnt);   /* c = 255 when the bit is 0 */
+            RSTEP(0) RSTEP(1) RSTEP(2) RSTEP(3) RSTEP(4) RSTEP(5) RSTEP(6) RSTEP(7)
+            RSTEP(8) RSTEP(9) RSTEP(10) RSTEP(11) RSTEP(12) RSTEP(13) RSTEP(14) RSTEP(15)
+#undef RSTEP
         }
     }
-    cp_async_wait<0>();
+    if (in_range) { A.used[gsafe * 2] = giY >> 2; A.used[gsafe * 2 + 1] = giC >> 2; }
     if (valid) {
         if (r1 == g.h) {
-            range_step(127u, range, cnt);                          // terminator: state 129, bit 0 (FFV1_Slice.cpp:334-343)
+            range_step(127u, 255u, range, cnt);                    // terminator: state 129, bit 0 (FFV1_Slice.cpp:334-343)
             // final flush of the coder (so that the decoder's BytesUsed() lands on the end, FFV1_Slice.cpp:297-299):
             // low += 0xFF in the current 16-bit window (stream bytes cnt, cnt+1), then two forced renormalisations
             uint32_t* W = reinterpret_cast<uint32_t*>(A.scratch + gsafe * A.slice_cap);
@@ -736,13 +751,13 @@ __global__ void __launch_bounds__(32) k_range(const __grid_constant__ EncArgs A,
             A.slice_size[gid] = cnt + 1;                           // cnt + 2 bytes produced; the last stays inside the coder
         } else {
             CoderState s;
-            s.low = 0; s.range = range; s.pending = 0; s.run = 0; s.pos = cnt; s.crc = 0; s.offY = 0; s.offC = 0;
+            s.range = range; s.pos = cnt;
             A.cstate[gid] = s;
         }
     }
 }
 
-// k_emit: grid (blocks of 256 coder-blocks, stream Y/C, frame*slice)
+// k_emit: grid (pieces of 256 x 64 records, stream Y/C, frame*slice)
 constexpr int kEmitThreads = 256;
 constexpr int kEmitWords = 22;          // local window: word 0 spare, then stream words (c0>>2)-1 ... (c0>>2)+19
 
@@ -754,23 +769,24 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ E
     const uint32_t blk = blockIdx.x * kEmitThreads + tid;
     if (blk >= used) return;
     const size_t cap = stream ? A.capC : A.capY;
-    const uint4* src = reinterpret_cast<const uint4*>((stream ? A.binsC : A.binsY) + (size_t)gid * cap) + (size_t)blk * 8;
-    const uint2 ck = (stream ? A.ckptC : A.ckptY)[(size_t)gid * (cap >> 6) + blk];
-    uint4 q[8];
+    const uint4* src = reinterpret_cast<const uint4*>((stream ? A.qC : A.qY) + (size_t)gid * cap) + (size_t)blk * 4;
+    const uint2 bw = *(reinterpret_cast<const uint2*>((stream ? A.bC : A.bY) + (size_t)gid * (cap >> 3)) + blk);
+    const uint2 ck = (stream ? A.ckptC : A.ckptY)[(size_t)gid * (cap / kCkptRecs) + blk];
+    uint4 q[4];
 #pragma unroll
-    for (int u = 0; u < 8; u++) q[u] = __ldg(src + u);
+    for (int u = 0; u < 4; u++) q[u] = __ldg(src + u);
 #pragma unroll
     for (int i = 0; i < kEmitWords; i++) s_loc[i][tid] = 0;
 
     uint32_t range = ck.x;
     const uint32_t c0 = ck.y;
-    // byte `lb` of the local window is stream byte 4*((c0>>2)-1) + lb - 4; the block starts at local byte 8 + (c0&3)
+    // byte `lb` of the local window is stream byte 4*((c0>>2)-1) + lb - 4; the piece starts at local byte 8 + (c0&3)
     uint32_t lpos = 8 + (c0 & 3);           // local byte index of the coder window's high byte
     uint64_t acc = 0;                       // bits 0..15 window, then pending bytes, then carry
     uint32_t nsh = 0;
     auto flush = [&](uint32_t extra) {
         // the value above the window (pending bytes + carry) has its LSB at the end of local byte lpos + nsh/8 - 1;
-        // `extra` = 16 also retires the window itself (end of block)
+        // `extra` = 16 also retires the window itself (end of the piece)
         const uint32_t k = nsh >> 3;
         const uint64_t V = extra ? acc : (acc >> 16);
         const uint32_t lb = lpos + k - 1 + (extra >> 3);
@@ -785,9 +801,8 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ E
         acc &= 0xFFFFull;
         nsh = 0;
     };
-    auto step = [&](uint32_t rec) {
-        const uint32_t sp = rec & 0x1FFu;
-        const uint32_t bit = (rec >> 9) & 1u;
+    auto step = [&](uint32_t qb, uint32_t bit) {
+        const uint32_t sp = qb + 1u;
         const uint32_t x = range * sp + (bit ? 0u : 255u);
         const uint32_t nr = x >> 8;
         acc += bit ? (uint64_t)(range - nr) : 0ull;
@@ -797,11 +812,14 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ E
         nsh += sh;
     };
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-        step(q[u].x & 0xFFFFu); step(q[u].x >> 16); step(q[u].y & 0xFFFFu); step(q[u].y >> 16);
-        flush(0);
-        step(q[u].z & 0xFFFFu); step(q[u].z >> 16); step(q[u].w & 0xFFFFu); step(q[u].w >> 16);
-        flush(0);
+    for (int u = 0; u < 4; u++) {
+        const uint32_t bits = (u < 2 ? bw.x : bw.y) >> ((u & 1) * 16);
+        const uint32_t ww[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            step((ww[k >> 2] >> ((k & 3) * 8)) & 255u, (bits >> k) & 1u);
+            if ((k & 3) == 3) flush(0);
+        }
     }
     flush(16);
     uint32_t* W = reinterpret_cast<uint32_t*>(A.scratch + (size_t)gid * A.slice_cap);
@@ -931,15 +949,17 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ E
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-cudaError_t configure_kernels(int nctx, int sstride, int wmax, int stage_cap) {
-    size_t need = model_smem_bytes(nctx, sstride, wmax, 2, stage_cap);
-    return cudaFuncSetAttribute(k_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+cudaError_t configure_kernels(const EncArgs& a) {
+    const size_t need = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.first_n, a.stage_cap);
+    if (a.sstride == 32) return cudaFuncSetAttribute(k_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    return cudaFuncSetAttribute(k_model_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }
 
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s) {
     dim3 grid(a.nslices * 2, nframes);
-    size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.stage_cap);
-    k_model<<<grid, kModelThreads, smem, s>>>(a, band);
+    const size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.first_n, a.stage_cap);
+    if (a.sstride == 32) k_model<<<grid, kModelThreads, smem, s>>>(a, band);
+    else k_model_compact<<<grid, kModelThreads, smem, s>>>(a, band);
     return cudaGetLastError();
 }
 
@@ -951,7 +971,7 @@ cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s
 
 cudaError_t launch_emit(const EncArgs& a, int nframes, cudaStream_t s) {
     int n = nframes * a.nslices;
-    const unsigned nblk = (unsigned)((a.capC >> 6) + kEmitThreads - 1) / kEmitThreads;
+    const unsigned nblk = (unsigned)((a.capC / kCkptRecs) + kEmitThreads - 1) / kEmitThreads;
     k_emit<<<dim3(nblk, 2, n), kEmitThreads, 0, s>>>(a);
     return cudaGetLastError();
 }
