@@ -154,13 +154,13 @@ constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
 template <bool kCompact>
 __host__ __device__ constexpr int cslot(int slot) { return kCompact ? slot - (slot > 10 ? 1 : 0) - (slot > 21 ? 2 : 0) : slot; }
 
+template <bool kRep>
 struct T1 {             // one_state lookup by q = sp - 1
     const uint8_t* base;    // replicated: + lane * 4 already applied
-    bool rep;
     __device__ __forceinline__ uint32_t operator()(uint32_t q) const {
-        if (rep) {
+        if (kRep) {
             const uint32_t w = *reinterpret_cast<const uint32_t*>(base + ((q & 0xFCu) << 5));
-            return (w >> ((q & 3u) * 8u)) & 255u;
+            return __byte_perm(w, 0, (q & 3u) | 0x4440u);
         }
         return base[q];
     }
@@ -168,10 +168,10 @@ struct T1 {             // one_state lookup by q = sp - 1
 
 // One bin on the register-resident state row: slot SLOT of the context whose states are in S. `used` lanes update the
 // state and write the record to *dst.
-template <bool kCompact, int SLOT>
-__device__ __forceinline__ void slot_step(uint32_t (&S)[8], bool used, bool bit, uint16_t* dst, const T1& t1) {
+template <bool kCompact, int SLOT, class TT>
+__device__ __forceinline__ void slot_step(const uint32_t (&S0)[8], uint32_t (&S)[8], bool used, bool bit, uint16_t* dst, const TT& t1) {
     constexpr int ci = cslot<kCompact>(SLOT), wi = ci >> 2, sh = (ci & 3) * 8;
-    const uint32_t st = (S[wi] >> sh) & 255u;
+    const uint32_t st = (S0[wi] >> sh) & 255u;
     const int s1 = bit ? 1 : -1;
     const uint32_t rec = (uint32_t)((int)st * s1 + 255);            // q | bit << 8
     const uint32_t n = t1(rec & 255u);                              // one_state[sp]
@@ -182,7 +182,7 @@ __device__ __forceinline__ void slot_step(uint32_t (&S)[8], bool used, bool bit,
     }
 }
 
-template <bool kCompact>
+template <bool kCompact, bool kRep>
 __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t* smem_raw) {
     const int slice = blockIdx.x >> 1, ps = blockIdx.x & 1, frame = blockIdx.y;
     const SliceGeom g = A.geom[slice];
@@ -196,13 +196,13 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     constexpr int kRow = kCompact ? 28 : 32;                   // state bytes per context
     constexpr int kWords = kCompact ? 7 : 8;
     const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, planes, A.first_n);
-    const bool rep = A.first_n > 0;
+    constexpr bool rep = kRep;
     const uint32_t first_n = (uint32_t)(A.first_n > 0 ? A.first_n : -A.first_n);
     const uint32_t fmask = first_n >= (uint32_t)A.nctx ? 0xFFFFu : first_n - 1u;
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
-    T1 t1;
-    t1.rep = rep;
+    T1<kRep> t1;
     t1.base = rep ? S.t1b + lane * 4 : S.t1b;
+    const uint32_t lt = (1u << lane) - 1u;
 
     const size_t fs = (size_t)frame * A.nslices + slice;
     const int state_bytes = (int)align16((size_t)A.nctx * kRow);
@@ -304,7 +304,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 if (c >= nchunk) break;
                 const int x = c * 32 + lane;
                 const bool valid = x < w;
-                uint32_t nb = 0;
+                uint32_t nb = 0, hh = 0x10000u + (uint32_t)lane;
                 if (valid) {
                     const int T = prv[x];
                     const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
@@ -321,8 +321,17 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                     d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
                     S.val[x] = d;
                     S.ctx[x] = (uint16_t)ctx;
-                    S.first[(uint32_t)ctx & fmask] = (uint16_t)x;            // some user of the context wins; settled below
+                    hh = (uint32_t)ctx & fmask;
                     nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
+                }
+                {   // claim of the context: inside the chunk the first user is known exactly (leader); between chunks some
+                    // leader's claim lands last and is corrected below. Non-leaders take the ordered path (S2b).
+                    const uint32_t m = __match_any_sync(0xffffffffu, hh);
+                    if (valid) {
+                        const bool leader = (m & lt) == 0;
+                        if (leader) S.first[hh] = (uint16_t)x;
+                        S.lflag[x] = leader ? (uint8_t)0 : (uint8_t)(1u + (S.ctx[x] & (uint32_t)(NW - 1)));
+                    }
                 }
                 uint32_t incl = nb;
 #pragma unroll
@@ -341,13 +350,23 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                     if (x < w) { dst[x] = nx0[k]; if (ps) dst[wmax + x] = nx1[k]; }
                 }
             }
-            // ---- S2p: a sample that comes before the recorded winner of its table entry poisons the entry: then every
-            // sample of the entry takes the ordered path (S2b). Entries whose winner is the first user stay as they are.
+            // ---- S2p: settle the claims between chunks: a leader that comes before the recorded claimant takes the entry; if
+            // after that an even earlier leader exists, it poisons the entry and every user of it takes the ordered path (S2b)
             for (int k = 0; k < KC; k++) {
                 const int c = k * NW + warp;
                 if (c >= nchunk) break;
                 const int x = c * 32 + lane;
-                if (x < w) {
+                if (x < w && S.lflag[x] == 0) {
+                    const uint32_t h = (uint32_t)S.ctx[x] & fmask;
+                    if ((uint32_t)S.first[h] > (uint32_t)x) S.first[h] = (uint16_t)x;
+                }
+            }
+            __syncthreads();
+            for (int k = 0; k < KC; k++) {
+                const int c = k * NW + warp;
+                if (c >= nchunk) break;
+                const int x = c * 32 + lane;
+                if (x < w && S.lflag[x] == 0) {
                     const uint32_t h = (uint32_t)S.ctx[x] & fmask;
                     if ((uint32_t)S.first[h] > (uint32_t)x) S.first[h] = (uint16_t)kPoison;
                 }
@@ -417,7 +436,11 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                         v = S.val[x];
                         cx = S.ctx[x];
                         o = extra + cb - segbase + S.off[x];
-                        win = (uint32_t)S.first[cx & fmask] == (uint32_t)x;
+#ifdef B200_ALL_SLOTLANE
+                        win = false;
+#else
+                        win = S.lflag[x] == 0 && (uint32_t)S.first[cx & fmask] == (uint32_t)x;
+#endif
                         if (!win) S.lflag[x] = (uint8_t)(1u + (cx & (uint32_t)(NW - 1)));
                     }
                     const bool nz = v != 0;
@@ -445,29 +468,38 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
 #pragma unroll
                         for (int i = 0; i < 8; i++) R[i] = 0x80808080u;
                     }
-                    slot_step<kCompact, 0>(R, win, !nz, pL, t1);
+                    uint32_t R0[8];     // the row as loaded: every single-use slot reads it, so the steps are independent of each other
+#pragma unroll
+                    for (int i = 0; i < 8; i++) R0[i] = R[i];
+                    slot_step<kCompact, 0>(R0, R, win, !nz, pL, t1);
                     // exponent, unary: bins 1 + i, i = 0..e (1 while i < e)
-#define EXP_STEP(i) if ((i) <= emax) slot_step<kCompact, 1 + (i)>(R, wnz && (i) <= e, (i) < e, pL + 1 + (i), t1);
-                    EXP_STEP(0) EXP_STEP(1) EXP_STEP(2) EXP_STEP(3) EXP_STEP(4) EXP_STEP(5) EXP_STEP(6) EXP_STEP(7) EXP_STEP(8)
+                    // (warp-uniform skips only in coarse groups: the steps inside a group are independent and overlap)
+#define EXP_STEP(i) slot_step<kCompact, 1 + (i)>(R0, R, wnz && (i) <= e, (i) < e, pL + 1 + (i), t1);
+                    if (emax >= 0) { EXP_STEP(0) EXP_STEP(1) EXP_STEP(2) EXP_STEP(3) }
+                    if (emax >= 4) { EXP_STEP(4) EXP_STEP(5) EXP_STEP(6) EXP_STEP(7) EXP_STEP(8) }
 #undef EXP_STEP
                     if (!kCompact) {
-                        for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, wnz && i <= e, i < e, pL + 1 + i, t1);
+                        for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, R, wnz && i <= e, i < e, pL + 1 + i, t1);
                     }
                     // sign: bin 2e + 2, slot 11 + min(e, 10)
-#define SGN_STEP(j) if ((j) >= emin && (j) <= emax) slot_step<kCompact, 11 + (j)>(R, wnz && e == (j), neg, pR, t1);
-                    SGN_STEP(0) SGN_STEP(1) SGN_STEP(2) SGN_STEP(3) SGN_STEP(4) SGN_STEP(5) SGN_STEP(6) SGN_STEP(7) SGN_STEP(8)
+#define SGN_STEP(j) slot_step<kCompact, 11 + (j)>(R0, R, wnz && e == (j), neg, pR, t1);
+                    if (emin <= 4 && emax >= 0) { SGN_STEP(0) SGN_STEP(1) SGN_STEP(2) SGN_STEP(3) SGN_STEP(4) }
+                    if (emin <= 8 && emax >= 5) { SGN_STEP(5) SGN_STEP(6) SGN_STEP(7) SGN_STEP(8) }
                     if (!kCompact) {
-                        SGN_STEP(9)
-                        if (emax >= 10) slot_step<kCompact, 21>(R, wnz && e >= 10, neg, pR, t1);
+                        if (emax >= 9) { SGN_STEP(9) }
+                        if (emax >= 10) slot_step<kCompact, 21>(R0, R, wnz && e >= 10, neg, pR, t1);
                     }
 #undef SGN_STEP
                     // mantissa, from the top bit down: bit i is bin 2e + 1 - i, slot 22 + min(i, 9)
                     if (!kCompact) {
-                        for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, wnz && i < e, (a >> i) & 1u, pR - 1 - i, t1);
+                        for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, R, wnz && i < e, (a >> i) & 1u, pR - 1 - i, t1);
                     }
-#define MAN_STEP(i) if ((i) < emax) slot_step<kCompact, 22 + (i)>(R, wnz && (i) < e, (a >> (i)) & 1u, pR - 1 - (i), t1);
-                    if (!kCompact) { MAN_STEP(8) }
-                    MAN_STEP(7) MAN_STEP(6) MAN_STEP(5) MAN_STEP(4) MAN_STEP(3) MAN_STEP(2) MAN_STEP(1) MAN_STEP(0)
+#define MAN_STEP(i) slot_step<kCompact, 22 + (i)>(R0, R, wnz && (i) < e, (a >> (i)) & 1u, pR - 1 - (i), t1);
+                    if (emax >= 5) {
+                        if (!kCompact) { MAN_STEP(8) }
+                        MAN_STEP(7) MAN_STEP(6) MAN_STEP(5) MAN_STEP(4)
+                    }
+                    if (emax >= 1) { MAN_STEP(3) MAN_STEP(2) MAN_STEP(1) MAN_STEP(0) }
 #undef MAN_STEP
                     if (win) {
                         if (!kCompact) {
@@ -491,17 +523,18 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                     const uint32_t fl = xl < w ? S.lflag[xl] : 0u;
                     uint32_t todo = __ballot_sync(0xffffffffu, fl == (uint32_t)(warp + 1));
                     if (!todo) continue;
-                    if (fl == (uint32_t)(warp + 1)) S.lflag[xl] = 0;
                     const uint32_t cb = extra + chunk_base(c) - segbase;
+                    const int my_v = xl < w ? S.val[xl] : 0;       // lane j holds sample j of the chunk
+                    const uint32_t my_co = xl < w ? ((uint32_t)S.ctx[xl] << 16) | S.off[xl] : 0u;
                     while (todo) {
                         const int j = __ffs(todo) - 1;
                         todo &= todo - 1;
-                        const int x = c * 32 + j;
-                        const int v = S.val[x];                 // warp-uniform
-                        const uint32_t ob = cb + S.off[x];
+                        const int v = __shfl_sync(0xffffffffu, my_v, j);                 // warp-uniform
+                        const uint32_t co = __shfl_sync(0xffffffffu, my_co, j);
+                        const uint32_t ob = cb + (co & 0xFFFFu);
                         const uint32_t a = (uint32_t)abs(v);
                         const int e = 31 - __clz(a | 1);
-                        uint8_t* sp = S.states + (size_t)S.ctx[x] * kRow + lslot;
+                        uint8_t* sp = S.states + (size_t)(co >> 16) * kRow + lslot;
                         if (e <= 8) {
                             const bool nz = v != 0;
                             const bool has = lane_has_slot && (lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e)));
@@ -539,7 +572,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                 *sp = (uint8_t)st;
                             }
                         }
-                        __syncwarp();
                     }
                 }
                 __syncthreads();
@@ -594,11 +626,15 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
 
 __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_body<false>(A, band, smem_raw);
+    k_model_body<false, true>(A, band, smem_raw);
+}
+__global__ void __launch_bounds__(kModelThreads, 1) k_model_lean(const __grid_constant__ EncArgs A, int band) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    k_model_body<false, false>(A, band, smem_raw);
 }
 __global__ void __launch_bounds__(kModelThreads, 1) k_model_compact(const __grid_constant__ EncArgs A, int band) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_body<true>(A, band, smem_raw);
+    k_model_body<true, false>(A, band, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -949,17 +985,25 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ E
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+typedef void (*model_fn)(const EncArgs, int);
+static model_fn pick_model(const EncArgs& a) { return a.sstride != 32 ? k_model_compact : (a.first_n > 0 ? k_model : k_model_lean); }
+
 cudaError_t configure_kernels(const EncArgs& a) {
     const size_t need = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.first_n, a.stage_cap);
-    if (a.sstride == 32) return cudaFuncSetAttribute(k_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-    return cudaFuncSetAttribute(k_model_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    // every kernel asks for the same L1 / shared-memory split as k_model: an SM cannot hold CTAs of two kernels that want
+    // different splits, and k_range / k_emit / k_pack must run beside k_model's CTAs, not after them
+    cudaFuncSetAttribute(k_range, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_pack, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(pick_model(a), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(pick_model(a), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }
 
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s) {
     dim3 grid(a.nslices * 2, nframes);
     const size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.first_n, a.stage_cap);
-    if (a.sstride == 32) k_model<<<grid, kModelThreads, smem, s>>>(a, band);
-    else k_model_compact<<<grid, kModelThreads, smem, s>>>(a, band);
+    pick_model(a)<<<grid, kModelThreads, smem, s>>>(a, band);
     return cudaGetLastError();
 }
 
