@@ -126,7 +126,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     const size_t chunk_need = 32 * (size_t)maxbins + b200::kMaxHeaderBins;
     size_t reserve = b200::kModelSmemReserve;
     if (const char* e = getenv("B200_SMEM_RESERVE")) reserve = (size_t)atoi(e);
-    const int tries[3] = {A.sstride == 32 ? S.nctx : 0, A.sstride == 32 ? 2048 : 0, -2048};
+    const int tries[3] = {A.sstride == 32 ? 1 : 0, -1, 0};    // one_state table replicated per bank, or plain
     int best = -1, best_nseg = 0;
     size_t best_cap = 0;
     for (int k = 0; k < 3; k++) {

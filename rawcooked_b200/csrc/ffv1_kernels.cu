@@ -74,7 +74,6 @@ __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, 
 // k_model a record is the 16-bit value q | bit << 8 = 255 + (bit ? state : -state); in global memory the q bytes and the
 // bits (one bit-plane, record r = bit r & 7 of byte r >> 3) are separate arrays.
 constexpr uint32_t kNopRec = 0x00FFu;
-constexpr uint32_t kPoison = 0xFFFEu;
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_model
@@ -85,36 +84,37 @@ constexpr uint32_t kPoison = 0xFFFEu;
 //   qtab    5 x 256 int16    quantisation tables
 //   t1      one_state, indexed by q: either replicated per bank ([64][32] words: lane l reads word (q >> 2) * 32 + l, no
 //           bank conflicts whatever the 32 lanes look up) or a plain 256-byte table when shared memory is short
-//   first   first-occurrence table: which sample of the plane-row is the first (in bitstream order) to use a context
-//   val/ctx/off/lflag per sample of the plane-row being coded: folded residual (after the context-sign flip), context,
-//           first record of the sample relative to its 32-sample chunk, leftover flag
+//   val/ctx/off per sample of the plane-row being coded: folded residual (after the context-sign flip), context, first
+//           record of the sample relative to its 32-sample chunk
 //   ctot    records per 32-sample chunk
+//   cmask   [chunk][class] which samples of the chunk belong to a context class (class = ctx mod 16 = owner warp)
 //   stage   the records of the plane-row (segment), 16 bit each, split into q bytes + bit-plane on the way out
 //
-// Per plane-row: S1 all samples in parallel: neighbours, context, residual, bin count, claim of the context ->
-// S2a every sample that is the FIRST user of its context in this row (all of them on grainy content): one lane per sample,
-// the 32 state bytes of the context in registers, all bins of the symbol -> S2b the other samples, in x order, by the warp
-// that owns the context class, one lane per slot -> S3 records to global memory.
+// Per plane-row: S1 all samples in parallel: neighbours, context, residual, bin count, class masks -> S2 (K3) warp q
+// resolves the adaptive states of the samples of class q, in bitstream order, 32 at a time: samples of one batch that use
+// distinct contexts go one per lane with the 32 state bytes of the context in registers (all bins of the symbol, the steps
+// of different slots overlap); repeated contexts wait for the next round of the batch; rounds with a few samples run one
+// sample per step with one lane per slot -> S3 records to global memory. Warps never share a context, so there is no
+// barrier inside S2.
 struct ModelSmem {
-    uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b; uint16_t* first;
-    int32_t* val; uint16_t* ctx; uint16_t* off; uint8_t* lflag; uint32_t* ctot; uint32_t* misc; uint16_t* stage;
+    uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b;
+    int32_t* val; uint16_t* ctx; uint16_t* off; uint32_t* ctot; uint32_t* cmask; uint32_t* misc; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 constexpr int kMaxChunks = 64;            // wmax <= 2048
 
-// bytes of everything except the record staging area. first_n < 0: t1 not replicated, |first_n| entries.
+// bytes of everything except the record staging area. first_n > 0: t1 replicated per bank.
 size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int first_n) {
     const bool rep = first_n > 0;
-    const int fn = first_n > 0 ? first_n : -first_n;
     size_t n = align16((size_t)nctx * sstride);
     n += align16((size_t)3 * planes * wmax * 4);
     n += 5 * 256 * 2;
     n += rep ? 64 * 32 * 4 : 256;
-    n += align16((size_t)fn * 2);
     n += align16((size_t)wmax * 4);          // val
     n += align16((size_t)wmax * 2) * 2;      // ctx, off
-    n += align16((size_t)wmax);              // lflag
-    n += kMaxChunks * 4 + 16 * 4;            // ctot, misc
+    n += kMaxChunks * 4;                     // ctot
+    n += kMaxChunks * kModelWarps * 4;       // cmask
+    n += 16 * 4;                             // misc
     return n;
 }
 size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int first_n, int stage_cap) {
@@ -123,24 +123,23 @@ size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int first_n
 
 __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes, int first_n) {
     const bool rep = first_n > 0;
-    const int fn = first_n > 0 ? first_n : -first_n;
     ModelSmem m;
     m.states = base; base += align16((size_t)nctx * sstride);
     m.ring = reinterpret_cast<int32_t*>(base); base += align16((size_t)3 * planes * wmax * 4);
     m.qtab = reinterpret_cast<int16_t*>(base); base += 5 * 256 * 2;
     m.t1w = reinterpret_cast<uint32_t*>(base); m.t1b = base; base += rep ? 64 * 32 * 4 : 256;
-    m.first = reinterpret_cast<uint16_t*>(base); base += align16((size_t)fn * 2);
     m.val = reinterpret_cast<int32_t*>(base); base += align16((size_t)wmax * 4);
     m.ctx = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
     m.off = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
-    m.lflag = base; base += align16((size_t)wmax);
     m.ctot = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * 4;
+    m.cmask = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * kModelWarps * 4;
     m.misc = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
     m.stage = reinterpret_cast<uint16_t*>(base);
     return m;
 }
 
 constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
+constexpr int kDenseMin = 6;            // rounds with fewer samples than this run one sample per step (one lane per slot)
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
@@ -166,18 +165,19 @@ struct T1 {             // one_state lookup by q = sp - 1
     }
 };
 
-// One bin on the register-resident state row: slot SLOT of the context whose states are in S. `used` lanes update the
-// state and write the record to *dst.
+// One bin on the register-resident state row: slot SLOT of the context. The state is read from S0 (the row as loaded,
+// or the running row for the two slots a symbol can use more than once), `used` lanes put the new state into S and write
+// the record to *dst.
 template <bool kCompact, int SLOT, class TT>
 __device__ __forceinline__ void slot_step(const uint32_t (&S0)[8], uint32_t (&S)[8], bool used, bool bit, uint16_t* dst, const TT& t1) {
-    constexpr int ci = cslot<kCompact>(SLOT), wi = ci >> 2, sh = (ci & 3) * 8;
-    const uint32_t st = (S0[wi] >> sh) & 255u;
+    constexpr int ci = cslot<kCompact>(SLOT), wi = ci >> 2, bi = ci & 3;
+    const uint32_t st = __byte_perm(S0[wi], 0, 0x4440 | bi);
     const int s1 = bit ? 1 : -1;
     const uint32_t rec = (uint32_t)((int)st * s1 + 255);            // q | bit << 8
     const uint32_t n = t1(rec & 255u);                              // one_state[sp]
     const uint32_t nx = (uint32_t)((int)n * s1 + (bit ? 0 : 256));  // bit ? one_state[st] : zero_state[st] = 256 - one_state[256 - st]
     if (used) {
-        S[wi] = (S[wi] & ~(255u << sh)) | (nx << sh);
+        S[wi] = __byte_perm(S[wi], nx, bi == 0 ? 0x3214 : bi == 1 ? 0x3240 : bi == 2 ? 0x3410 : 0x4210);
         *dst = (uint16_t)rec;
     }
 }
@@ -196,12 +196,9 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     constexpr int kRow = kCompact ? 28 : 32;                   // state bytes per context
     constexpr int kWords = kCompact ? 7 : 8;
     const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, planes, A.first_n);
-    constexpr bool rep = kRep;
-    const uint32_t first_n = (uint32_t)(A.first_n > 0 ? A.first_n : -A.first_n);
-    const uint32_t fmask = first_n >= (uint32_t)A.nctx ? 0xFFFFu : first_n - 1u;
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
     T1<kRep> t1;
-    t1.base = rep ? S.t1b + lane * 4 : S.t1b;
+    t1.base = kRep ? S.t1b + lane * 4 : S.t1b;
     const uint32_t lt = (1u << lane) - 1u;
 
     const size_t fs = (size_t)frame * A.nslices + slice;
@@ -218,12 +215,12 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
             for (int i = tid; i < n16; i += kModelThreads) d[i] = s[i];
         }
         for (int i = tid; i < 5 * 256; i += kModelThreads) S.qtab[i] = A.qtab[i];
-        if (rep) {
+        if (kRep) {
             for (int i = tid; i < 64 * 32; i += kModelThreads) S.t1w[i] = reinterpret_cast<const uint32_t*>(A.t1q)[i >> 5];
         } else {
             for (int i = tid; i < 256; i += kModelThreads) S.t1b[i] = A.t1q[i];
         }
-        for (int i = tid; i < wmax; i += kModelThreads) S.lflag[i] = 0;
+        for (int i = tid; i < kMaxChunks * NW; i += kModelThreads) S.cmask[i] = 0;
     }
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
@@ -268,9 +265,9 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     __syncthreads();
 
     const int nchunk = (w + 31) >> 5;
-    const int KC = (nchunk + NW - 1) / NW;  // 32-sample chunks per warp: chunk c belongs to warp c % NW
+    const int KC = (nchunk + NW - 1) / NW;  // 32-sample chunks per warp in S1: chunk c belongs to warp c % NW
     const int sbits = A.sbits;
-    // slot-per-lane path: lane -> slot class of the symbol binarisation (rangecoder::s, FFV1_RangeCoder.cpp:135-171):
+    // one-lane-per-slot path: lane -> slot class of the symbol binarisation (rangecoder::s, FFV1_RangeCoder.cpp:135-171):
     //   lane 0 zero flag | 1..10 exponent i = lane-1 (slot 10 also takes i > 9) | 11..21 sign for e = lane-11 |
     //   22..31 mantissa bit i = lane-22 (slot 31 also takes i > 9)
     const bool isB = lane >= 1 && lane <= 10, isD = lane >= 11 && lane <= 21;
@@ -298,13 +295,13 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
             const int32_t* cur = S.ring + ((size_t)((y + 3) % 3) * planes + pl) * wmax;
             const int32_t* prv = S.ring + ((size_t)((y + 2) % 3) * planes + pl) * wmax;
             const int32_t* pp2 = S.ring + ((size_t)((y + 1) % 3) * planes + pl) * wmax;
-            // ---- S1 (K2): prediction, context, fold, records per sample; claim of the context
+            // ---- S1 (K2): prediction, context, fold, records per sample; class masks
             for (int k = 0; k < KC; k++) {
                 const int c = k * NW + warp;
                 if (c >= nchunk) break;
                 const int x = c * 32 + lane;
                 const bool valid = x < w;
-                uint32_t nb = 0, hh = 0x10000u + (uint32_t)lane;
+                uint32_t nb = 0, cls = 32u + (uint32_t)lane;
                 if (valid) {
                     const int T = prv[x];
                     const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
@@ -321,22 +318,17 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                     d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
                     S.val[x] = d;
                     S.ctx[x] = (uint16_t)ctx;
-                    hh = (uint32_t)ctx & fmask;
+                    cls = (uint32_t)ctx & (uint32_t)(NW - 1);
                     nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
-                }
-                {   // claim of the context: inside the chunk the first user is known exactly (leader); between chunks some
-                    // leader's claim lands last and is corrected below. Non-leaders take the ordered path (S2b).
-                    const uint32_t m = __match_any_sync(0xffffffffu, hh);
-                    if (valid) {
-                        const bool leader = (m & lt) == 0;
-                        if (leader) S.first[hh] = (uint16_t)x;
-                        S.lflag[x] = leader ? (uint8_t)0 : (uint8_t)(1u + (S.ctx[x] & (uint32_t)(NW - 1)));
-                    }
                 }
                 uint32_t incl = nb;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                if (valid) S.off[x] = (uint16_t)(incl - nb);
+                const uint32_t m = __match_any_sync(0xffffffffu, cls);
+                if (valid) {
+                    S.off[x] = (uint16_t)(incl - nb);
+                    if ((m & lt) == 0) S.cmask[c * NW + cls] = m;              // lowest lane of the class group
+                }
                 if (lane == 31) S.ctot[c] = incl;
             }
             __syncthreads();
@@ -348,27 +340,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 for (int k = 0; k < kMaxPixPerThread; k++) {
                     const int x = tid + k * kModelThreads;
                     if (x < w) { dst[x] = nx0[k]; if (ps) dst[wmax + x] = nx1[k]; }
-                }
-            }
-            // ---- S2p: settle the claims between chunks: a leader that comes before the recorded claimant takes the entry; if
-            // after that an even earlier leader exists, it poisons the entry and every user of it takes the ordered path (S2b)
-            for (int k = 0; k < KC; k++) {
-                const int c = k * NW + warp;
-                if (c >= nchunk) break;
-                const int x = c * 32 + lane;
-                if (x < w && S.lflag[x] == 0) {
-                    const uint32_t h = (uint32_t)S.ctx[x] & fmask;
-                    if ((uint32_t)S.first[h] > (uint32_t)x) S.first[h] = (uint16_t)x;
-                }
-            }
-            __syncthreads();
-            for (int k = 0; k < KC; k++) {
-                const int c = k * NW + warp;
-                if (c >= nchunk) break;
-                const int x = c * 32 + lane;
-                if (x < w && S.lflag[x] == 0) {
-                    const uint32_t h = (uint32_t)S.ctx[x] & fmask;
-                    if ((uint32_t)S.first[h] > (uint32_t)x) S.first[h] = (uint16_t)kPoison;
                 }
             }
             // exclusive prefix of the chunk totals, every warp for itself: lane l holds chunks l and l + 32
@@ -412,7 +383,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 }
                 if (start < nchunk) { if (tid == 0) atomicOr(A.flags, 4u); sc[nsg] = nchunk; }
             }
-            __syncthreads();
             PHASE_MARK(1);
 
             const uint32_t rc_base = ((uint32_t)(fs * A.band_rows + (y - r0)) * 3u + (uint32_t)(ps ? 1 + pl : 0)) * (uint32_t)A.nseg;
@@ -421,93 +391,176 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 const uint32_t extra = s == 0 ? seg_extra : 0u;
                 const uint32_t segbase = chunk_base(c0);
                 const uint32_t seg_total = extra + chunk_base(c1) - segbase;
-                // ---- S2a (K3): first users of their context, one lane per sample, state row in registers
-                for (int k = 0; k < KC; k++) {
-                    const int c = k * NW + warp;
-                    if (c >= nchunk) break;
-                    if (c < c0 || c >= c1) continue;
-                    const int x = c * 32 + lane;
-                    const bool valid = x < w;
-                    int v = 0;
-                    uint32_t cx = 0, o = 0;
-                    bool win = false;
-                    const uint32_t cb = chunk_base(c);
-                    if (valid) {
-                        v = S.val[x];
-                        cx = S.ctx[x];
-                        o = extra + cb - segbase + S.off[x];
-#ifdef B200_ALL_SLOTLANE
-                        win = false;
-#else
-                        win = S.lflag[x] == 0 && (uint32_t)S.first[cx & fmask] == (uint32_t)x;
-#endif
-                        if (!win) S.lflag[x] = (uint8_t)(1u + (cx & (uint32_t)(NW - 1)));
-                    }
-                    const bool nz = v != 0;
-                    const uint32_t a = (uint32_t)abs(v);
-                    const int e = nz ? 31 - __clz(a) : -1;
-                    const int emax = __reduce_max_sync(0xffffffffu, win ? e : -1);
-                    if (!__any_sync(0xffffffffu, win)) continue;
-                    const int emin = __reduce_min_sync(0xffffffffu, (win && nz) ? e : 99);
-                    const bool neg = v < 0;
-                    const bool wnz = win && nz;
-                    uint16_t* pL = S.stage + o;
-                    uint16_t* pR = pL + (2 * e + 2);
-                    uint32_t R[8];
-                    uint8_t* row = S.states + (size_t)cx * kRow;
-                    if (win) {
-                        if (!kCompact) {
-                            const uint4 q0 = reinterpret_cast<const uint4*>(row)[0], q1 = reinterpret_cast<const uint4*>(row)[1];
-                            R[0] = q0.x; R[1] = q0.y; R[2] = q0.z; R[3] = q0.w; R[4] = q1.x; R[5] = q1.y; R[6] = q1.z; R[7] = q1.w;
-                        } else {
+                const uint32_t rel = extra - segbase;          // record offset of a sample = rel + chunk base + off[x]
+                // ---- S2 (K3): warp q = context class q. Its samples of this segment, in x order, 32 per batch.
+                {
+                    // masks of my class: lane l holds chunks l and l + 32
+                    const bool in0 = lane >= c0 && lane < c1, in1 = lane + 32 >= c0 && lane + 32 < c1;
+                    const uint32_t M0 = in0 ? S.cmask[lane * NW + warp] : 0u, M1 = in1 ? S.cmask[(lane + 32) * NW + warp] : 0u;
+                    if (in0) S.cmask[lane * NW + warp] = 0;
+                    if (in1) S.cmask[(lane + 32) * NW + warp] = 0;
+                    const uint32_t n0 = __popc(M0), n1 = __popc(M1);
+                    uint32_t q0 = n0, q1 = n1;
 #pragma unroll
-                            for (int i = 0; i < kWords; i++) R[i] = reinterpret_cast<const uint32_t*>(row)[i];
-                            R[7] = 0;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t a0 = __shfl_up_sync(0xffffffffu, q0, o), a1 = __shfl_up_sync(0xffffffffu, q1, o);
+                        if (lane >= o) { q0 += a0; q1 += a1; }
+                    }
+                    const uint32_t cnt0 = __shfl_sync(0xffffffffu, q0, 31);
+                    const uint32_t P0 = q0 - n0, P1 = cnt0 + q1 - n1;           // samples of my class before chunk l / l + 32
+                    const uint32_t mine = cnt0 + __shfl_sync(0xffffffffu, q1, 31);
+                    for (uint32_t b0 = 0; b0 < mine; b0 += 32) {
+                        const uint32_t k = b0 + lane;
+                        const bool have = k < mine;
+                        // the chunk of sample k: the last chunk whose prefix is <= k (binary search over the 64 prefixes)
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int st = 32; st; st >>= 1) {
+                            const uint32_t t = c + st;
+                            const uint32_t p0 = __shfl_sync(0xffffffffu, P0, t & 31), p1 = __shfl_sync(0xffffffffu, P1, t & 31);
+                            const uint32_t pt = t < 32 ? p0 : p1;
+                            if (t < 64 && pt <= k) c = t;
                         }
-                    } else {
+                        const uint32_t m0 = __shfl_sync(0xffffffffu, M0, c & 31), m1 = __shfl_sync(0xffffffffu, M1, c & 31);
+                        const uint32_t pc0 = __shfl_sync(0xffffffffu, P0, c & 31), pc1 = __shfl_sync(0xffffffffu, P1, c & 31);
+                        const uint32_t e0 = __shfl_sync(0xffffffffu, ex0, c & 31), e1 = __shfl_sync(0xffffffffu, ex1, c & 31);
+                        uint32_t mc = c < 32 ? m0 : m1;
+                        uint32_t r = k - (c < 32 ? pc0 : pc1);
+                        int v = 0;
+                        uint32_t cx = 0x10000u + (uint32_t)lane, o = 0;
+                        if (have) {
+                            while (r) { mc &= mc - 1; r--; }
+                            const int x = (int)(c * 32u) + __ffs(mc) - 1;
+                            v = S.val[x];
+                            cx = S.ctx[x];
+                            o = rel + (c < 32 ? e0 : e1) + S.off[x];
+                        }
+                        // rounds: samples of the batch that share a context go one after the other
+                        const uint32_t mm = __match_any_sync(0xffffffffu, cx);
+                        const int rank = __popc(mm & lt);
+                        const int maxr = __reduce_max_sync(0xffffffffu, have ? rank : 0);
+                        const bool nz = v != 0;
+                        const uint32_t a = (uint32_t)abs(v);
+                        const int e = nz ? 31 - __clz(a) : -1;
+                        const bool neg = v < 0;
+                        for (int rr = 0; rr <= maxr; rr++) {
+                            const bool act = have && rank == rr;
+                            const uint32_t am = __ballot_sync(0xffffffffu, act);
+                            if (__popc(am) >= kDenseMin) {
+                                // ---- one lane per sample, state row in registers
+                                const int emax = __reduce_max_sync(0xffffffffu, act ? e : -1);
+                                const int emin = __reduce_min_sync(0xffffffffu, (act && nz) ? e : 99);
+                                const bool wnz = act && nz;
+                                uint16_t* pL = S.stage + o;
+                                uint16_t* pR = pL + (2 * e + 2);
+                                uint32_t R[8], R0[8];
+                                uint8_t* row = S.states + (size_t)(cx & 0xFFFFu) * kRow;
+                                if (act) {
+                                    if (!kCompact) {
+                                        const uint4 w0 = reinterpret_cast<const uint4*>(row)[0], w1 = reinterpret_cast<const uint4*>(row)[1];
+                                        R[0] = w0.x; R[1] = w0.y; R[2] = w0.z; R[3] = w0.w; R[4] = w1.x; R[5] = w1.y; R[6] = w1.z; R[7] = w1.w;
+                                    } else {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) R[i] = 0x80808080u;
-                    }
-                    uint32_t R0[8];     // the row as loaded: every single-use slot reads it, so the steps are independent of each other
+                                        for (int i = 0; i < kWords; i++) R[i] = reinterpret_cast<const uint32_t*>(row)[i];
+                                        R[7] = 0;
+                                    }
+                                } else {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) R0[i] = R[i];
-                    slot_step<kCompact, 0>(R0, R, win, !nz, pL, t1);
-                    // exponent, unary: bins 1 + i, i = 0..e (1 while i < e)
-                    // (warp-uniform skips only in coarse groups: the steps inside a group are independent and overlap)
+                                    for (int i = 0; i < 8; i++) R[i] = 0x80808080u;
+                                }
+#pragma unroll
+                                for (int i = 0; i < 8; i++) R0[i] = R[i];
+                                slot_step<kCompact, 0>(R0, R, act, !nz, pL, t1);
+                                // exponent, unary: bins 1 + i, i = 0..e (1 while i < e)
+                                // (warp-uniform skips only in coarse groups: the steps inside a group are independent and overlap)
 #define EXP_STEP(i) slot_step<kCompact, 1 + (i)>(R0, R, wnz && (i) <= e, (i) < e, pL + 1 + (i), t1);
-                    if (emax >= 0) { EXP_STEP(0) EXP_STEP(1) EXP_STEP(2) EXP_STEP(3) }
-                    if (emax >= 4) { EXP_STEP(4) EXP_STEP(5) EXP_STEP(6) EXP_STEP(7) EXP_STEP(8) }
+                                if (emax >= 0) { EXP_STEP(0) EXP_STEP(1) EXP_STEP(2) EXP_STEP(3) }
+                                if (emax >= 4) { EXP_STEP(4) EXP_STEP(5) EXP_STEP(6) EXP_STEP(7) EXP_STEP(8) }
 #undef EXP_STEP
-                    if (!kCompact) {
-                        for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, R, wnz && i <= e, i < e, pL + 1 + i, t1);
-                    }
-                    // sign: bin 2e + 2, slot 11 + min(e, 10)
+                                if (!kCompact) {
+                                    for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, R, wnz && i <= e, i < e, pL + 1 + i, t1);
+                                }
+                                // sign: bin 2e + 2, slot 11 + min(e, 10)
 #define SGN_STEP(j) slot_step<kCompact, 11 + (j)>(R0, R, wnz && e == (j), neg, pR, t1);
-                    if (emin <= 4 && emax >= 0) { SGN_STEP(0) SGN_STEP(1) SGN_STEP(2) SGN_STEP(3) SGN_STEP(4) }
-                    if (emin <= 8 && emax >= 5) { SGN_STEP(5) SGN_STEP(6) SGN_STEP(7) SGN_STEP(8) }
-                    if (!kCompact) {
-                        if (emax >= 9) { SGN_STEP(9) }
-                        if (emax >= 10) slot_step<kCompact, 21>(R0, R, wnz && e >= 10, neg, pR, t1);
-                    }
+                                if (emin <= 4 && emax >= 0) { SGN_STEP(0) SGN_STEP(1) SGN_STEP(2) SGN_STEP(3) SGN_STEP(4) }
+                                if (emin <= 8 && emax >= 5) { SGN_STEP(5) SGN_STEP(6) SGN_STEP(7) SGN_STEP(8) }
+                                if (!kCompact) {
+                                    if (emax >= 9) { SGN_STEP(9) }
+                                    if (emax >= 10) slot_step<kCompact, 21>(R0, R, wnz && e >= 10, neg, pR, t1);
+                                }
 #undef SGN_STEP
-                    // mantissa, from the top bit down: bit i is bin 2e + 1 - i, slot 22 + min(i, 9)
-                    if (!kCompact) {
-                        for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, R, wnz && i < e, (a >> i) & 1u, pR - 1 - i, t1);
-                    }
+                                // mantissa, from the top bit down: bit i is bin 2e + 1 - i, slot 22 + min(i, 9)
+                                if (!kCompact) {
+                                    for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, R, wnz && i < e, (a >> i) & 1u, pR - 1 - i, t1);
+                                }
 #define MAN_STEP(i) slot_step<kCompact, 22 + (i)>(R0, R, wnz && (i) < e, (a >> (i)) & 1u, pR - 1 - (i), t1);
-                    if (emax >= 5) {
-                        if (!kCompact) { MAN_STEP(8) }
-                        MAN_STEP(7) MAN_STEP(6) MAN_STEP(5) MAN_STEP(4)
-                    }
-                    if (emax >= 1) { MAN_STEP(3) MAN_STEP(2) MAN_STEP(1) MAN_STEP(0) }
+                                if (emax >= 5) {
+                                    if (!kCompact) { MAN_STEP(8) }
+                                    MAN_STEP(7) MAN_STEP(6) MAN_STEP(5) MAN_STEP(4)
+                                }
+                                if (emax >= 1) { MAN_STEP(3) MAN_STEP(2) MAN_STEP(1) MAN_STEP(0) }
 #undef MAN_STEP
-                    if (win) {
-                        if (!kCompact) {
-                            reinterpret_cast<uint4*>(row)[0] = make_uint4(R[0], R[1], R[2], R[3]);
-                            reinterpret_cast<uint4*>(row)[1] = make_uint4(R[4], R[5], R[6], R[7]);
-                        } else {
+                                if (act) {
+                                    if (!kCompact) {
+                                        reinterpret_cast<uint4*>(row)[0] = make_uint4(R[0], R[1], R[2], R[3]);
+                                        reinterpret_cast<uint4*>(row)[1] = make_uint4(R[4], R[5], R[6], R[7]);
+                                    } else {
 #pragma unroll
-                            for (int i = 0; i < kWords; i++) reinterpret_cast<uint32_t*>(row)[i] = R[i];
+                                        for (int i = 0; i < kWords; i++) reinterpret_cast<uint32_t*>(row)[i] = R[i];
+                                    }
+                                }
+                            } else {
+                                // ---- a few samples: one per step, lane s = slot s of the context (slots are independent chains)
+                                uint32_t todo = am;
+                                while (todo) {
+                                    const int j = __ffs(todo) - 1;
+                                    todo &= todo - 1;
+                                    const int vj = __shfl_sync(0xffffffffu, v, j);                 // warp-uniform
+                                    const uint32_t cj = __shfl_sync(0xffffffffu, cx, j);
+                                    const uint32_t ob = __shfl_sync(0xffffffffu, o, j);
+                                    const uint32_t aj = (uint32_t)abs(vj);
+                                    const int ej = 31 - __clz(aj | 1);
+                                    uint8_t* sp = S.states + (size_t)cj * kRow + lslot;
+                                    if (ej <= 8) {
+                                        const bool nzj = vj != 0;
+                                        const bool has = lane_has_slot && (lane == 0 ? true : (nzj && (isB ? li <= ej : isD ? li == ej : li < ej)));
+                                        const bool bit = lane == 0 ? !nzj : isB ? (li < ej) : isD ? (vj < 0) : (((aj >> li) & 1u) != 0);
+                                        const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * ej + 2 : 2 * ej + 1 - li;
+                                        if (has) {
+                                            const uint32_t st = *sp;
+                                            const int s1 = bit ? 1 : -1;
+                                            const uint32_t rec = (uint32_t)((int)st * s1 + 255);
+                                            S.stage[ob + idx] = (uint16_t)rec;
+                                            *sp = (uint8_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
+                                        }
+                                    } else {
+                                        int n2 = 0, i0b = 0, step = 0;     // n2 bins; bin k uses index i = i0b + k*step
+                                        if (lane == 0) n2 = 1;
+                                        else if (lane <= 9) { n2 = 1; i0b = lane - 1; }
+                                        else if (lane == 10) { n2 = ej - 8; i0b = 9; step = 1; }
+                                        else if (lane <= 21) { n2 = (lane - 11) == min(ej, 10); }
+                                        else if (lane <= 30) { n2 = 1; i0b = lane - 22; }
+                                        else { n2 = ej - 9; i0b = ej - 1; step = -1; }
+                                        if (n2) {
+                                            uint32_t st = *sp;
+                                            for (int kk = 0; kk < n2; kk++) {
+                                                const int i = i0b + kk * step;
+                                                bool bit; uint32_t idx;
+                                                if (lane == 0) { bit = false; idx = 0; }
+                                                else if (lane <= 10) { bit = i < ej; idx = 1 + i; }
+                                                else if (lane <= 21) { bit = vj < 0; idx = 2 * ej + 2; }
+                                                else { bit = ((aj >> i) & 1u) != 0; idx = 2 * ej + 1 - i; }
+                                                const int s1 = bit ? 1 : -1;
+                                                const uint32_t rec = (uint32_t)((int)st * s1 + 255);
+                                                S.stage[ob + idx] = (uint16_t)rec;
+                                                st = (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
+                                            }
+                                            *sp = (uint8_t)st;
+                                        }
+                                    }
+                                }
+                            }
+                            __syncwarp();       // the next round / batch reads the state rows this one wrote
                         }
                     }
                 }
@@ -516,66 +569,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 if ((uint32_t)tid < padded - seg_total) S.stage[seg_total + tid] = (uint16_t)kNopRec;
                 __syncthreads();
                 PHASE_MARK(2);
-                // ---- S2b: the other samples, in x order: warp q walks the samples of context class q (ctx mod NW), one sample
-                // per step, lane s = slot s of the context (slots are independent chains)
-                for (int c = c0; c < c1; c++) {
-                    const int xl = c * 32 + lane;
-                    const uint32_t fl = xl < w ? S.lflag[xl] : 0u;
-                    uint32_t todo = __ballot_sync(0xffffffffu, fl == (uint32_t)(warp + 1));
-                    if (!todo) continue;
-                    const uint32_t cb = extra + chunk_base(c) - segbase;
-                    const int my_v = xl < w ? S.val[xl] : 0;       // lane j holds sample j of the chunk
-                    const uint32_t my_co = xl < w ? ((uint32_t)S.ctx[xl] << 16) | S.off[xl] : 0u;
-                    while (todo) {
-                        const int j = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const int v = __shfl_sync(0xffffffffu, my_v, j);                 // warp-uniform
-                        const uint32_t co = __shfl_sync(0xffffffffu, my_co, j);
-                        const uint32_t ob = cb + (co & 0xFFFFu);
-                        const uint32_t a = (uint32_t)abs(v);
-                        const int e = 31 - __clz(a | 1);
-                        uint8_t* sp = S.states + (size_t)(co >> 16) * kRow + lslot;
-                        if (e <= 8) {
-                            const bool nz = v != 0;
-                            const bool has = lane_has_slot && (lane == 0 ? true : (nz && (isB ? li <= e : isD ? li == e : li < e)));
-                            const bool bit = lane == 0 ? !nz : isB ? (li < e) : isD ? (v < 0) : (((a >> li) & 1u) != 0);
-                            const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * e + 2 : 2 * e + 1 - li;
-                            if (has) {
-                                const uint32_t st = *sp;
-                                const int s1 = bit ? 1 : -1;
-                                const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                S.stage[ob + idx] = (uint16_t)rec;
-                                *sp = (uint8_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
-                            }
-                        } else {
-                            int n2 = 0, i0b = 0, step = 0;     // n2 bins; bin k uses index i = i0b + k*step
-                            if (lane == 0) n2 = 1;
-                            else if (lane <= 9) { n2 = 1; i0b = lane - 1; }
-                            else if (lane == 10) { n2 = e - 8; i0b = 9; step = 1; }
-                            else if (lane <= 21) { n2 = (lane - 11) == min(e, 10); }
-                            else if (lane <= 30) { n2 = 1; i0b = lane - 22; }
-                            else { n2 = e - 9; i0b = e - 1; step = -1; }
-                            if (n2) {
-                                uint32_t st = *sp;
-                                for (int k = 0; k < n2; k++) {
-                                    const int i = i0b + k * step;
-                                    bool bit; uint32_t idx;
-                                    if (lane == 0) { bit = false; idx = 0; }
-                                    else if (lane <= 10) { bit = i < e; idx = 1 + i; }
-                                    else if (lane <= 21) { bit = v < 0; idx = 2 * e + 2; }
-                                    else { bit = ((a >> i) & 1u) != 0; idx = 2 * e + 1 - i; }
-                                    const int s1 = bit ? 1 : -1;
-                                    const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                    S.stage[ob + idx] = (uint16_t)rec;
-                                    st = (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
-                                }
-                                *sp = (uint8_t)st;
-                            }
-                        }
-                    }
-                }
-                __syncthreads();
-                PHASE_MARK(3);
                 // ---- S3: staged records -> global: q bytes and bit-plane, whole blocks, coalesced
                 {
                     const uint32_t ngrp = padded >> 4;          // groups of 16 records; a multiple of 8
@@ -605,7 +598,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                     bins_total += seg_total - extra;
                 }
                 if (s + 1 < nsg) __syncthreads();
-                PHASE_MARK(4);
+                PHASE_MARK(3);
             }
             if (tid == 0) for (int s = nsg; s < A.nseg; s++) A.rowcnt[rc_base + s] = 0;
             seg_extra = 0;
@@ -1009,7 +1002,10 @@ cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s
 
 cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s) {
     int n = nframes * a.nslices;
-    k_range<<<(n + 31) / 32, 32, 0, s>>>(a, band, nframes);
+    // k_range is one latency-critical warp per CTA: beside k_model's warps (or more than two of its own kind per scheduler) it
+    // slows down by the scheduler's round-robin factor. The (unused) dynamic shared memory keeps it at 8 CTAs per SM and off
+    // the SMs k_model occupies; its high-priority stream hands it the first SMs k_model's CTAs leave.
+    k_range<<<(n + 31) / 32, 32, 28 * 1024, s>>>(a, band, nframes);
     return cudaGetLastError();
 }
 
