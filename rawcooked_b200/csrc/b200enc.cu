@@ -49,6 +49,8 @@ struct b200_ffv1_enc {
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> tev;   // timing mode: 4 events per band + 2 around the pack kernels
+    std::vector<cudaEvent_t> trace; // B200_TRACE: [band][model start, model end, range start, range end, emit start, emit end] on the kernels' own streams
+    bool trace_pending = false;
     bool timed_pending = false;
     uint64_t stats[8] = {0};
     int last_frames = 0;
@@ -220,12 +222,11 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     A.geom = d_geom; A.qtab = d_qtab; A.t1q = d_trans; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
     A1 = A;
     A1.qY = qY1; A1.qC = qC1; A1.bY = bY1; A1.bC = bC1; A1.rowcnt = rc1; A1.ckptY = kY1; A1.ckptC = kC1; A1.used = us1;
-    // the serial coder and the emitter must never wait behind queued model CTAs: their streams get the higher priority
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaStreamCreateWithPriority(&E->sm, cudaStreamNonBlocking, prio_lo);
-    cudaStreamCreateWithPriority(&E->sr, cudaStreamNonBlocking, prio_hi);
-    cudaStreamCreateWithPriority(&E->se, cudaStreamNonBlocking, prio_hi);
+    // equal priorities: with prioritised streams the device preempts k_model's CTAs (227 KB of state each) whenever
+    // k_range / k_emit become runnable, which costs more than it gains (measured: 28.5 ms per band against 21 ms)
+    cudaStreamCreateWithFlags(&E->sm, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&E->sr, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&E->se, cudaStreamNonBlocking);
     for (cudaEvent_t* ev : {&E->ev_start, &E->ev_model[0], &E->ev_model[1], &E->ev_range[0], &E->ev_range[1], &E->ev_emit[0],
                             &E->ev_emit[1], &E->ev_done_m, &E->ev_done_e})
         cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -289,6 +290,13 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
         for (auto& ev : E->tev) CU(cudaEventCreate(&ev));
     }
     const bool tm = E->timing;
+    const bool tr = !serial && getenv("B200_TRACE") != nullptr;
+    if (tr && E->trace.empty()) {
+        E->trace.resize((size_t)A[0].nbands * 6 + 1);
+        for (auto& ev : E->trace) CU(cudaEventCreate(&ev));
+    }
+    if (tr) CU(cudaEventRecord(E->trace[(size_t)A[0].nbands * 6], s));
+    E->trace_pending = tr;
     cudaStream_t sm = serial ? s : E->sm, sr = serial ? s : E->sr, se = serial ? s : E->se;
     uint64_t launches = 0;
     if (!serial) {
@@ -302,13 +310,19 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
         const int p = band & 1;
         if (!serial && band >= 2) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 0], s));
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 0], sm));
         CU(b200::launch_model(A[p], band, n_frames, sm));
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 1], sm));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 1], s));
         if (!serial) { CU(cudaEventRecord(E->ev_model[p], sm)); CU(cudaStreamWaitEvent(sr, E->ev_model[p], 0)); }
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 2], sr));
         CU(b200::launch_range(A[p], band, n_frames, sr));
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 3], sr));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 2], s));
         if (!serial) { CU(cudaEventRecord(E->ev_range[p], sr)); CU(cudaStreamWaitEvent(se, E->ev_range[p], 0)); }
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 4], se));
         CU(b200::launch_emit(A[p], n_frames, se));
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 5], se));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 3], s));
         if (!serial) CU(cudaEventRecord(E->ev_emit[p], se));
         launches += 3;
@@ -337,6 +351,17 @@ static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* 
     if (getenv("B200_PHASE_TIMING")) {
         const unsigned long long* ph = reinterpret_cast<const unsigned long long*>(E->h_flags + 16);
         fprintf(stderr, "k_model phase cycles (sum over CTAs): S1 %llu S2p %llu S2a %llu S2b %llu S3 %llu\n", ph[0], ph[1], ph[2], ph[3], ph[4]);
+    }
+    if (E->trace_pending) {
+        const int nb = A.nbands;
+        const cudaEvent_t t0 = E->trace[(size_t)nb * 6];
+        fprintf(stderr, "band: model start-end | range start-end | emit start-end (ms)\n");
+        for (int b = 0; b < nb; b++) {
+            float v[6];
+            for (int k = 0; k < 6; k++) { cudaEventSynchronize(E->trace[b * 6 + k]); cudaEventElapsedTime(&v[k], t0, E->trace[b * 6 + k]); }
+            fprintf(stderr, "%2d: %7.2f-%7.2f | %7.2f-%7.2f | %7.2f-%7.2f\n", b, v[0], v[1], v[2], v[3], v[4], v[5]);
+        }
+        E->trace_pending = false;
     }
     if (E->h_flags[0] & 1u) return fail(B200_ERR_OVERFLOW, "slice scratch overflow");
     if (E->h_flags[0] & 2u) return fail(B200_ERR_OVERFLOW, "packet arena overflow");

@@ -139,7 +139,7 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
 }
 
 constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
-constexpr int kDenseMin = 6;            // rounds with fewer samples than this run one sample per step (one lane per slot)
+constexpr int kDenseMin = 10;           // rounds with fewer samples than this run one sample per step (one lane per slot)
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
@@ -153,33 +153,37 @@ constexpr int kDenseMin = 6;            // rounds with fewer samples than this r
 template <bool kCompact>
 __host__ __device__ constexpr int cslot(int slot) { return kCompact ? slot - (slot > 10 ? 1 : 0) - (slot > 21 ? 2 : 0) : slot; }
 
+// shared-memory accesses by 32-bit shared address (no generic-address conversion per access)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8_volatile(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 template <bool kRep>
-struct T1 {             // one_state lookup by q = sp - 1
-    const uint8_t* base;    // replicated: + lane * 4 already applied
+struct T1 {             // one_state lookup by q = sp - 1 (the table never changes after the kernel's prologue)
+    uint32_t base;          // shared address; replicated: + lane * 4 already applied
     __device__ __forceinline__ uint32_t operator()(uint32_t q) const {
-        if (kRep) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(base + ((q & 0xFCu) << 5));
-            return __byte_perm(w, 0, (q & 3u) | 0x4440u);
-        }
-        return base[q];
+        if (kRep) return __byte_perm(lds_u32(base + ((q & 0xFCu) << 5)), 0, (q & 3u) | 0x4440u);
+        return lds_u8(base + q);
     }
 };
 
 // One bin on the register-resident state row: slot SLOT of the context. The state is read from S0 (the row as loaded,
 // or the running row for the two slots a symbol can use more than once), `used` lanes put the new state into S and write
-// the record to *dst.
+// the record to shared address dst (the other lanes write to `dummy`). Branch-free.
 template <bool kCompact, int SLOT, class TT>
-__device__ __forceinline__ void slot_step(const uint32_t (&S0)[8], uint32_t (&S)[8], bool used, bool bit, uint16_t* dst, const TT& t1) {
+__device__ __forceinline__ void slot_step(const uint32_t (&S0)[8], uint32_t (&S)[8], bool used, bool bit, uint32_t dst, uint32_t dummy, const TT& t1) {
     constexpr int ci = cslot<kCompact>(SLOT), wi = ci >> 2, bi = ci & 3;
     const uint32_t st = __byte_perm(S0[wi], 0, 0x4440 | bi);
     const int s1 = bit ? 1 : -1;
     const uint32_t rec = (uint32_t)((int)st * s1 + 255);            // q | bit << 8
     const uint32_t n = t1(rec & 255u);                              // one_state[sp]
     const uint32_t nx = (uint32_t)((int)n * s1 + (bit ? 0 : 256));  // bit ? one_state[st] : zero_state[st] = 256 - one_state[256 - st]
-    if (used) {
-        S[wi] = __byte_perm(S[wi], nx, bi == 0 ? 0x3214 : bi == 1 ? 0x3240 : bi == 2 ? 0x3410 : 0x4210);
-        *dst = (uint16_t)rec;
-    }
+    const uint32_t ins = __byte_perm(S[wi], nx, bi == 0 ? 0x3214 : bi == 1 ? 0x3240 : bi == 2 ? 0x3410 : 0x4210);
+    S[wi] = used ? ins : S[wi];
+    sts_u16(used ? dst : dummy, rec);
 }
 
 template <bool kCompact, bool kRep>
@@ -198,7 +202,9 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, planes, A.first_n);
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
     T1<kRep> t1;
-    t1.base = kRep ? S.t1b + lane * 4 : S.t1b;
+    t1.base = smem_addr(S.t1b) + (kRep ? lane * 4 : 0);
+    const uint32_t dummy = smem_addr(S.misc) + lane * 2;    // where the lanes that have no bin in a step put their record
+    const uint32_t stage_a = smem_addr(S.stage), states_a = smem_addr(S.states);
     const uint32_t lt = (1u << lane) - 1u;
 
     const size_t fs = (size_t)frame * A.nslices + slice;
@@ -318,7 +324,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                     d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
                     S.val[x] = d;
                     S.ctx[x] = (uint16_t)ctx;
-                    cls = (uint32_t)ctx & (uint32_t)(NW - 1);
+                    cls = ((uint32_t)ctx * 2654435761u) >> (32 - (NW == 16 ? 4 : 5));   // multiplicative hash: even class sizes
                     nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
                 }
                 uint32_t incl = nb;
@@ -451,8 +457,8 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                 const int emax = __reduce_max_sync(0xffffffffu, act ? e : -1);
                                 const int emin = __reduce_min_sync(0xffffffffu, (act && nz) ? e : 99);
                                 const bool wnz = act && nz;
-                                uint16_t* pL = S.stage + o;
-                                uint16_t* pR = pL + (2 * e + 2);
+                                const uint32_t pL = stage_a + o * 2u;
+                                const uint32_t pR = pL + (uint32_t)(2 * e + 2) * 2u;
                                 uint32_t R[8], R0[8];
                                 uint8_t* row = S.states + (size_t)(cx & 0xFFFFu) * kRow;
                                 if (act) {
@@ -470,30 +476,30 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                 }
 #pragma unroll
                                 for (int i = 0; i < 8; i++) R0[i] = R[i];
-                                slot_step<kCompact, 0>(R0, R, act, !nz, pL, t1);
+                                slot_step<kCompact, 0>(R0, R, act, !nz, pL, dummy, t1);
                                 // exponent, unary: bins 1 + i, i = 0..e (1 while i < e)
                                 // (warp-uniform skips only in coarse groups: the steps inside a group are independent and overlap)
-#define EXP_STEP(i) slot_step<kCompact, 1 + (i)>(R0, R, wnz && (i) <= e, (i) < e, pL + 1 + (i), t1);
+#define EXP_STEP(i) slot_step<kCompact, 1 + (i)>(R0, R, wnz && (i) <= e, (i) < e, pL + 2 * (1 + (i)), dummy, t1);
                                 if (emax >= 0) { EXP_STEP(0) EXP_STEP(1) EXP_STEP(2) EXP_STEP(3) }
                                 if (emax >= 4) { EXP_STEP(4) EXP_STEP(5) EXP_STEP(6) EXP_STEP(7) EXP_STEP(8) }
 #undef EXP_STEP
                                 if (!kCompact) {
-                                    for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, R, wnz && i <= e, i < e, pL + 1 + i, t1);
+                                    for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, R, wnz && i <= e, i < e, pL + 2 * (1 + i), dummy, t1);
                                 }
                                 // sign: bin 2e + 2, slot 11 + min(e, 10)
-#define SGN_STEP(j) slot_step<kCompact, 11 + (j)>(R0, R, wnz && e == (j), neg, pR, t1);
+#define SGN_STEP(j) slot_step<kCompact, 11 + (j)>(R0, R, wnz && e == (j), neg, pR, dummy, t1);
                                 if (emin <= 4 && emax >= 0) { SGN_STEP(0) SGN_STEP(1) SGN_STEP(2) SGN_STEP(3) SGN_STEP(4) }
                                 if (emin <= 8 && emax >= 5) { SGN_STEP(5) SGN_STEP(6) SGN_STEP(7) SGN_STEP(8) }
                                 if (!kCompact) {
                                     if (emax >= 9) { SGN_STEP(9) }
-                                    if (emax >= 10) slot_step<kCompact, 21>(R0, R, wnz && e >= 10, neg, pR, t1);
+                                    if (emax >= 10) slot_step<kCompact, 21>(R0, R, wnz && e >= 10, neg, pR, dummy, t1);
                                 }
 #undef SGN_STEP
                                 // mantissa, from the top bit down: bit i is bin 2e + 1 - i, slot 22 + min(i, 9)
                                 if (!kCompact) {
-                                    for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, R, wnz && i < e, (a >> i) & 1u, pR - 1 - i, t1);
+                                    for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, R, wnz && i < e, (a >> i) & 1u, pR - 2 * (1 + i), dummy, t1);
                                 }
-#define MAN_STEP(i) slot_step<kCompact, 22 + (i)>(R0, R, wnz && (i) < e, (a >> (i)) & 1u, pR - 1 - (i), t1);
+#define MAN_STEP(i) slot_step<kCompact, 22 + (i)>(R0, R, wnz && (i) < e, (a >> (i)) & 1u, pR - 2 * (1 + (i)), dummy, t1);
                                 if (emax >= 5) {
                                     if (!kCompact) { MAN_STEP(8) }
                                     MAN_STEP(7) MAN_STEP(6) MAN_STEP(5) MAN_STEP(4)
@@ -520,18 +526,18 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                     const uint32_t ob = __shfl_sync(0xffffffffu, o, j);
                                     const uint32_t aj = (uint32_t)abs(vj);
                                     const int ej = 31 - __clz(aj | 1);
-                                    uint8_t* sp = S.states + (size_t)cj * kRow + lslot;
-                                    if (ej <= 8) {
+                                    const uint32_t sp = states_a + cj * (uint32_t)kRow + (uint32_t)lslot;
+                                    if (ej <= 9) {     // every lane has at most one bin
                                         const bool nzj = vj != 0;
                                         const bool has = lane_has_slot && (lane == 0 ? true : (nzj && (isB ? li <= ej : isD ? li == ej : li < ej)));
                                         const bool bit = lane == 0 ? !nzj : isB ? (li < ej) : isD ? (vj < 0) : (((aj >> li) & 1u) != 0);
                                         const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * ej + 2 : 2 * ej + 1 - li;
                                         if (has) {
-                                            const uint32_t st = *sp;
+                                            const uint32_t st = lds_u8_volatile(sp);
                                             const int s1 = bit ? 1 : -1;
                                             const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                            S.stage[ob + idx] = (uint16_t)rec;
-                                            *sp = (uint8_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
+                                            sts_u16(stage_a + (ob + (uint32_t)idx) * 2u, rec);
+                                            sts_u8(sp, (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256)));
                                         }
                                     } else {
                                         int n2 = 0, i0b = 0, step = 0;     // n2 bins; bin k uses index i = i0b + k*step
@@ -542,7 +548,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                         else if (lane <= 30) { n2 = 1; i0b = lane - 22; }
                                         else { n2 = ej - 9; i0b = ej - 1; step = -1; }
                                         if (n2) {
-                                            uint32_t st = *sp;
+                                            uint32_t st = lds_u8_volatile(sp);
                                             for (int kk = 0; kk < n2; kk++) {
                                                 const int i = i0b + kk * step;
                                                 bool bit; uint32_t idx;
@@ -552,10 +558,10 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                                 else { bit = ((aj >> i) & 1u) != 0; idx = 2 * ej + 1 - i; }
                                                 const int s1 = bit ? 1 : -1;
                                                 const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                                S.stage[ob + idx] = (uint16_t)rec;
+                                                sts_u16(stage_a + (ob + idx) * 2u, rec);
                                                 st = (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
                                             }
-                                            *sp = (uint8_t)st;
+                                            sts_u8(sp, st);
                                         }
                                     }
                                 }
