@@ -40,6 +40,8 @@ struct b200_ffv1_enc {
     b200::EncArgs args;             // band buffers of parity 0
     b200::EncArgs args1;            // same, band buffers of parity 1 (double buffering across the three kernel streams)
     cudaStream_t sm = nullptr, sr = nullptr, se = nullptr;   // model / range / emit streams
+    cudaStream_t sc = nullptr;                               // host-to-device copies of the host entry point
+    std::vector<cudaEvent_t> ev_h2d;                         // [band] rows of the band have arrived
     cudaEvent_t ev_start = nullptr, ev_model[2] = {nullptr, nullptr}, ev_range[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr};
     cudaEvent_t ev_done_m = nullptr, ev_done_e = nullptr;
     int max_frames = 0;
@@ -227,6 +229,9 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     cudaStreamCreateWithFlags(&E->sm, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&E->sr, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&E->se, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&E->sc, cudaStreamNonBlocking);
+    E->ev_h2d.resize(A.nbands);
+    for (auto& ev : E->ev_h2d) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (cudaEvent_t* ev : {&E->ev_start, &E->ev_model[0], &E->ev_model[1], &E->ev_range[0], &E->ev_range[1], &E->ev_emit[0],
                             &E->ev_emit[1], &E->ev_done_m, &E->ev_done_e})
         cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -252,7 +257,8 @@ void b200_ffv1_close(b200_ffv1_enc* E) {
     for (cudaEvent_t ev : {E->ev_start, E->ev_model[0], E->ev_model[1], E->ev_range[0], E->ev_range[1], E->ev_emit[0], E->ev_emit[1],
                            E->ev_done_m, E->ev_done_e})
         if (ev) cudaEventDestroy(ev);
-    for (cudaStream_t st : {E->sm, E->sr, E->se}) if (st) cudaStreamDestroy(st);
+    for (auto& ev : E->ev_h2d) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {E->sm, E->sr, E->se, E->sc}) if (st) cudaStreamDestroy(st);
     delete E;
 }
 
@@ -271,10 +277,9 @@ int b200_ffv1_set_timing(b200_ffv1_enc* E, int32_t enabled) {
     return 0;
 }
 
-int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, void* stream) {
-    if (!E || !d_frames) return fail(B200_ERR_INVALID, "null argument");
-    if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+// host_frames != nullptr: the payloads are still in host memory; they are copied to d_frames band by band on the copy stream,
+// each band's rows just ahead of the k_model launch that needs them, so that the transfer hides behind the kernels
+static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, cudaStream_t s, const uint8_t* const* host_frames) {
     CU(cudaSetDevice(E->cfg.device));
     b200::EncArgs A[2] = {E->args, E->args1};
     A[0].in = A[1].in = static_cast<const uint8_t*>(d_frames);
@@ -306,8 +311,28 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
         CU(cudaStreamWaitEvent(se, E->ev_start, 0));
     }
     const int nb = A[0].nbands;
+    std::vector<std::pair<int, int>> srows;                      // distinct (y0, h) of the slice grid's rows
+    if (host_frames) {
+        for (const auto& g : E->st.slices)
+            if (srows.empty() || srows.back().first != g.y0) srows.push_back({g.y0, g.h});
+        if (!serial) { CU(cudaEventRecord(E->ev_start, s)); CU(cudaStreamWaitEvent(E->sc, E->ev_start, 0)); }
+    }
     for (int band = 0; band < nb; band++) {
         const int p = band & 1;
+        if (host_frames) {
+            cudaStream_t sc = serial ? s : E->sc;
+            const size_t rb = E->st.row_bytes;
+            for (int i = 0; i < n_frames; i++)
+                for (const auto& sr_ : srows) {
+                    const int r0 = band * A[0].band_rows;
+                    if (r0 >= sr_.second) continue;
+                    const int r1 = r0 + A[0].band_rows < sr_.second ? r0 + A[0].band_rows : sr_.second;
+                    const size_t o = (size_t)(sr_.first + r0) * rb;
+                    CU(cudaMemcpyAsync((uint8_t*)d_frames + (size_t)i * E->st.frame_bytes + o, host_frames[i] + o, (size_t)(r1 - r0) * rb,
+                                       cudaMemcpyHostToDevice, sc));
+                }
+            if (!serial) { CU(cudaEventRecord(E->ev_h2d[band], sc)); CU(cudaStreamWaitEvent(sm, E->ev_h2d[band], 0)); }
+        }
         if (!serial && band >= 2) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 0], s));
         if (tr) CU(cudaEventRecord(E->trace[band * 6 + 0], sm));
@@ -342,6 +367,12 @@ int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_fr
     E->stats[0] = launches;
     E->stats[2] = (uint64_t)n_frames * E->st.width * E->st.height * 3;
     return 0;
+}
+
+int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, void* stream) {
+    if (!E || !d_frames) return fail(B200_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
+    return encode_impl(E, d_frames, n_frames, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* out_len, uint64_t* total) {
@@ -422,11 +453,9 @@ int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_
     CU(cudaSetDevice(E->cfg.device));
     const size_t fb = E->st.frame_bytes;
     if (!E->d_in) CU(cudaMalloc((void**)&E->d_in, fb * E->max_frames));
-    for (int i = 0; i < n_frames; i++) {
+    for (int i = 0; i < n_frames; i++)
         if (!frames[i]) return fail(B200_ERR_INVALID, "null frame pointer");
-        CU(cudaMemcpyAsync(E->d_in + (size_t)i * fb, frames[i], fb, cudaMemcpyHostToDevice, 0));
-    }
-    int r = b200_ffv1_encode_device(E, E->d_in, n_frames, nullptr);
+    int r = encode_impl(E, E->d_in, n_frames, nullptr, frames);
     if (r) return r;
     CU(cudaStreamSynchronize(0));
     return b200_ffv1_fetch_packets(E, out, out_cap, out_off, out_len, n_frames);
