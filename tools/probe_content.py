@@ -1,5 +1,5 @@
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from rawcooked_b200 import ffv1, synth as S
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
