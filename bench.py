@@ -208,7 +208,7 @@ def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from rawcooked_b200 import ffv1, synth as S
+    from rawcooked_b200 import dist as D, ffv1, synth as S
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -235,21 +235,13 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     def gather_to_rank0():
-        """NCCL exchange of the encoded packets: lengths first, then the bytes of every rank's arena to rank 0."""
+        """NCCL exchange of the encoded packets (rawcooked_b200/dist.py): lengths first, then every rank's arena to rank 0."""
         arena, off, ln = enc.packets_device(F)
         total = off[-1] + ln[-1]
         mine = torch.as_tensor(_CudaBuf(arena, total), device=dev)
-        lens = torch.tensor([total], dtype=torch.int64, device=dev)
-        all_lens = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(all_lens, lens)
-        if rank == 0:
-            bufs = [torch.empty(int(all_lens[r].item()), dtype=torch.uint8, device=dev) for r in range(1, world)]
-            reqs = [dist.irecv(bufs[r - 1], src=r) for r in range(1, world)]
-            for q in reqs:
-                q.wait()
-            return total + sum(b.numel() for b in bufs)
-        dist.send(mine, dst=0)
-        return total
+        lens = torch.tensor(ln, dtype=torch.int64, device=dev)
+        got = D.gather_packets(mine, lens, rank, world, F)
+        return sum(int(a.numel()) for a, _ in got) if got is not None else total
 
     def step_device():
         enc.encode_device(d_frames.data_ptr(), F, stream.cuda_stream)
@@ -347,7 +339,7 @@ def run_b200(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload_config(F, world),
             "e2e": {"value": e2e, "unit": "MPix/s", "h2d_bytes_per_step": F * fb * world, "d2h_bytes_per_step": int(out_bytes) * world,
-                    "api": "b200_ffv1_encode_host (pinned host frames -> packets in pinned host memory)", "fps": e2e * 1e6 / (W * H)},
+                    "api": "b200_ffv1_encode_host (pinned host frames -> packets in pinned host memory; H2D band by band behind the kernels)", "fps": e2e * 1e6 / (W * H)},
             "gpu_launches": int(st["launches"]) * args.steps * world,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -373,7 +365,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=int(os.environ.get("B200_BENCH_FRAMES", "64")), help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=int(os.environ.get("B200_BENCH_FRAMES", "128")), help="frames per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
