@@ -139,7 +139,10 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
 }
 
 constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
-constexpr int kDenseMin = 10;           // rounds with fewer samples than this run one sample per step (one lane per slot)
+#ifndef B200_DENSE_MIN
+#define B200_DENSE_MIN 3      // measured on B200: 1 -> 219 ms, 3 -> 202, 5 -> 210, 7 -> 226, 10 -> 247, 16 -> 287 per 64 4K frames
+#endif
+constexpr int kDenseMin = B200_DENSE_MIN;           // rounds with fewer samples than this run one sample per step (one lane per slot)
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
