@@ -38,11 +38,12 @@ struct b200_ffv1_enc {
     b200_ffv1_cfg cfg;
     b200::Ffv1Stream st;
     b200::EncArgs args;             // band buffers of parity 0
-    b200::EncArgs args1;            // same, band buffers of parity 1 (double buffering across the three kernel streams)
+    static constexpr int kPar = 2;  // band-buffer sets in rotation (3 measured slower on B200: the extra model launches starve k_range of SMs)
+    b200::EncArgs argsN[kPar];      // [0] unused (= args); [p] same as args with the band buffers of set p
     cudaStream_t sm = nullptr, sr = nullptr, se = nullptr;   // model / range / emit streams
     cudaStream_t sc = nullptr;                               // host-to-device copies of the host entry point
     std::vector<cudaEvent_t> ev_h2d;                         // [band] rows of the band have arrived
-    cudaEvent_t ev_start = nullptr, ev_model[2] = {nullptr, nullptr}, ev_range[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr, ev_model[kPar] = {}, ev_range[kPar] = {}, ev_emit[kPar] = {};
     cudaEvent_t ev_done_m = nullptr, ev_done_e = nullptr;
     int max_frames = 0;
     std::vector<void*> owned;       // device allocations
@@ -188,7 +189,6 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(d_hc, hc.size() * 4);
     ALLOC(d_crc, 1024);
     ALLOC(A.state_save, (size_t)B * ns * 2 * (((size_t)S.nctx * A.sstride + 15) & ~(size_t)15));
-    b200::EncArgs& A1 = E->args1;
     ALLOC(A.qY, (size_t)B * ns * A.capY);
     ALLOC(A.qC, (size_t)B * ns * A.capC);
     ALLOC(A.bY, (size_t)B * ns * (A.capY >> 3));
@@ -197,15 +197,17 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(A.ckptY, (size_t)B * ns * (A.capY >> 6) * 8);
     ALLOC(A.ckptC, (size_t)B * ns * (A.capC >> 6) * 8);
     ALLOC(A.used, (size_t)B * ns * 2 * 4);
-    uint8_t *qY1, *qC1, *bY1, *bC1; uint32_t *rc1, *us1; uint2 *kY1, *kC1;
-    ALLOC(qY1, (size_t)B * ns * A.capY);
-    ALLOC(qC1, (size_t)B * ns * A.capC);
-    ALLOC(bY1, (size_t)B * ns * (A.capY >> 3));
-    ALLOC(bC1, (size_t)B * ns * (A.capC >> 3));
-    ALLOC(rc1, (size_t)B * ns * A.band_rows * 3 * A.nseg * 4);
-    ALLOC(kY1, (size_t)B * ns * (A.capY >> 6) * 8);
-    ALLOC(kC1, (size_t)B * ns * (A.capC >> 6) * 8);
-    ALLOC(us1, (size_t)B * ns * 2 * 4);
+    for (int pz = 1; pz < b200_ffv1_enc::kPar; pz++) {
+        b200::EncArgs& P = E->argsN[pz];
+        ALLOC(P.qY, (size_t)B * ns * A.capY);
+        ALLOC(P.qC, (size_t)B * ns * A.capC);
+        ALLOC(P.bY, (size_t)B * ns * (A.capY >> 3));
+        ALLOC(P.bC, (size_t)B * ns * (A.capC >> 3));
+        ALLOC(P.rowcnt, (size_t)B * ns * A.band_rows * 3 * A.nseg * 4);
+        ALLOC(P.ckptY, (size_t)B * ns * (A.capY >> 6) * 8);
+        ALLOC(P.ckptC, (size_t)B * ns * (A.capC >> 6) * 8);
+        ALLOC(P.used, (size_t)B * ns * 2 * 4);
+    }
     ALLOC(A.cstate, (size_t)B * ns * sizeof(b200::CoderState));
     ALLOC(A.scratch, (size_t)B * ns * A.slice_cap);
     ALLOC(A.slice_size, (size_t)B * ns * 4);
@@ -222,8 +224,12 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     cudaMemcpy(d_hc, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d_crc, b200::crc32_mpeg_table(), 1024, cudaMemcpyHostToDevice);
     A.geom = d_geom; A.qtab = d_qtab; A.t1q = d_trans; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
-    A1 = A;
-    A1.qY = qY1; A1.qC = qC1; A1.bY = bY1; A1.bC = bC1; A1.rowcnt = rc1; A1.ckptY = kY1; A1.ckptC = kC1; A1.used = us1;
+    for (int pz = 1; pz < b200_ffv1_enc::kPar; pz++) {
+        const b200::EncArgs P = E->argsN[pz];
+        E->argsN[pz] = A;
+        b200::EncArgs& Q = E->argsN[pz];
+        Q.qY = P.qY; Q.qC = P.qC; Q.bY = P.bY; Q.bC = P.bC; Q.rowcnt = P.rowcnt; Q.ckptY = P.ckptY; Q.ckptC = P.ckptC; Q.used = P.used;
+    }
     // equal priorities: with prioritised streams the device preempts k_model's CTAs (227 KB of state each) whenever
     // k_range / k_emit become runnable, which costs more than it gains (measured: 28.5 ms per band against 21 ms)
     cudaStreamCreateWithFlags(&E->sm, cudaStreamNonBlocking);
@@ -232,9 +238,9 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     cudaStreamCreateWithFlags(&E->sc, cudaStreamNonBlocking);
     E->ev_h2d.resize(A.nbands);
     for (auto& ev : E->ev_h2d) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    for (cudaEvent_t* ev : {&E->ev_start, &E->ev_model[0], &E->ev_model[1], &E->ev_range[0], &E->ev_range[1], &E->ev_emit[0],
-                            &E->ev_emit[1], &E->ev_done_m, &E->ev_done_e})
-        cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    for (cudaEvent_t* ev : {&E->ev_start, &E->ev_done_m, &E->ev_done_e}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    for (int pz = 0; pz < b200_ffv1_enc::kPar; pz++)
+        for (cudaEvent_t* ev : {&E->ev_model[pz], &E->ev_range[pz], &E->ev_emit[pz]}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     cudaError_t e2 = cudaHostAlloc((void**)&E->h_flags, 256, cudaHostAllocDefault);
     if (e2 != cudaSuccess) { int rc = fail_cuda(e2, "cudaHostAlloc"); b200_ffv1_close(E); return rc; }
     for (auto& ev : E->ev) cudaEventCreate(&ev);
@@ -254,9 +260,9 @@ void b200_ffv1_close(b200_ffv1_enc* E) {
     if (E->h_flags) cudaFreeHost(E->h_flags);
     for (auto& ev : E->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : E->tev) if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : {E->ev_start, E->ev_model[0], E->ev_model[1], E->ev_range[0], E->ev_range[1], E->ev_emit[0], E->ev_emit[1],
-                           E->ev_done_m, E->ev_done_e})
-        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {E->ev_start, E->ev_done_m, E->ev_done_e}) if (ev) cudaEventDestroy(ev);
+    for (int pz = 0; pz < b200_ffv1_enc::kPar; pz++)
+        for (cudaEvent_t ev : {E->ev_model[pz], E->ev_range[pz], E->ev_emit[pz]}) if (ev) cudaEventDestroy(ev);
     for (auto& ev : E->ev_h2d) if (ev) cudaEventDestroy(ev);
     for (cudaStream_t st : {E->sm, E->sr, E->se, E->sc}) if (st) cudaStreamDestroy(st);
     delete E;
@@ -281,8 +287,11 @@ int b200_ffv1_set_timing(b200_ffv1_enc* E, int32_t enabled) {
 // each band's rows just ahead of the k_model launch that needs them, so that the transfer hides behind the kernels
 static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, cudaStream_t s, const uint8_t* const* host_frames) {
     CU(cudaSetDevice(E->cfg.device));
-    b200::EncArgs A[2] = {E->args, E->args1};
-    A[0].in = A[1].in = static_cast<const uint8_t*>(d_frames);
+    constexpr int kPar = b200_ffv1_enc::kPar;
+    b200::EncArgs A[kPar];
+    A[0] = E->args;
+    for (int pz = 1; pz < kPar; pz++) A[pz] = E->argsN[pz];
+    for (int pz = 0; pz < kPar; pz++) A[pz].in = static_cast<const uint8_t*>(d_frames);
     CU(cudaMemsetAsync(A[0].flags, 0, 256, s));
     CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)n_frames * A[0].nslices * A[0].slice_cap, s));   // k_emit accumulates into it
     // Three kernels per band on three streams: model(b) -> range(b) -> emit(b); model(b) reuses the band buffers of
@@ -318,7 +327,7 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
         if (!serial) { CU(cudaEventRecord(E->ev_start, s)); CU(cudaStreamWaitEvent(E->sc, E->ev_start, 0)); }
     }
     for (int band = 0; band < nb; band++) {
-        const int p = band & 1;
+        const int p = band % kPar;
         if (host_frames) {
             cudaStream_t sc = serial ? s : E->sc;
             const size_t rb = E->st.row_bytes;
@@ -333,7 +342,7 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
                 }
             if (!serial) { CU(cudaEventRecord(E->ev_h2d[band], sc)); CU(cudaStreamWaitEvent(sm, E->ev_h2d[band], 0)); }
         }
-        if (!serial && band >= 2) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
+        if (!serial && band >= kPar) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 0], s));
         if (tr) CU(cudaEventRecord(E->trace[band * 6 + 0], sm));
         CU(b200::launch_model(A[p], band, n_frames, sm));
