@@ -30,18 +30,20 @@ def gather_packets(arena, lens, rank, world, max_frames_per_rank):
     if rank != 0:
         total = int(lens.sum().item())
         if total:
-            dist.send(arena[:total].contiguous(), dst=0)
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, arena[:total].contiguous(), 0)]):
+                q.wait()
         return None
     out = [(arena[:int(lens.sum().item())], lens)]
-    bufs, reqs = [], []
+    bufs, ops = [], []
     for r in range(1, world):
         ln = all_lens[r][:int(all_n[r].item())]
         buf = torch.empty(int(ln.sum().item()), dtype=torch.uint8, device=dev)
         bufs.append((buf, ln))
         if buf.numel():
-            reqs.append(dist.irecv(buf, src=r))
-    for q in reqs:
-        q.wait()
+            ops.append(dist.P2POp(dist.irecv, buf, r))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):      # one grouped NCCL launch (ncclGroupStart/End) for all the senders
+            q.wait()
     return out + bufs
 
 
