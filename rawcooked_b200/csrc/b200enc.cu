@@ -179,12 +179,18 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     uint8_t t1q[256];                                               // one_state indexed by q = sp - 1
     for (int i = 0; i < 255; i++) t1q[i] = S.one_state[i + 1];
     t1q[255] = 0;
+    uint8_t tpow[5][256];                                           // one_state iterated 2^i times (runs of zero residuals)
+    for (int i = 0; i < 256; i++) tpow[0][i] = i ? S.one_state[i] : 0;
+    for (int k = 1; k < 5; k++)
+        for (int i = 0; i < 256; i++) tpow[k][i] = tpow[k - 1][tpow[k - 1][i]];
 
     b200::SliceGeom* d_geom; int16_t* d_qtab; uint8_t* d_trans; uint16_t* d_hb; int32_t* d_hc; uint32_t* d_crc;
 #define ALLOC(p, n) do { cudaError_t e_ = dalloc(&(p), (n), own); if (e_ != cudaSuccess) { int rc_ = fail_cuda(e_, "cudaMalloc " #p); b200_ffv1_close(E); return rc_; } } while (0)
     ALLOC(d_geom, sizeof(b200::SliceGeom) * ns);
     ALLOC(d_qtab, sizeof S.qtab);
     ALLOC(d_trans, 256);
+    uint8_t* d_tpow;
+    ALLOC(d_tpow, sizeof tpow);
     ALLOC(d_hb, hb.size() * 2);
     ALLOC(d_hc, hc.size() * 4);
     ALLOC(d_crc, 1024);
@@ -220,10 +226,11 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     cudaMemcpy(d_geom, S.slices.data(), sizeof(b200::SliceGeom) * ns, cudaMemcpyHostToDevice);
     cudaMemcpy(d_qtab, S.qtab, sizeof S.qtab, cudaMemcpyHostToDevice);
     cudaMemcpy(d_trans, t1q, 256, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_tpow, tpow, sizeof tpow, cudaMemcpyHostToDevice);
     cudaMemcpy(d_hb, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(d_hc, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d_crc, b200::crc32_mpeg_table(), 1024, cudaMemcpyHostToDevice);
-    A.geom = d_geom; A.qtab = d_qtab; A.t1q = d_trans; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
+    A.geom = d_geom; A.qtab = d_qtab; A.t1q = d_trans; A.tpow = d_tpow; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
     for (int pz = 1; pz < b200_ffv1_enc::kPar; pz++) {
         const b200::EncArgs P = E->argsN[pz];
         E->argsN[pz] = A;

@@ -98,7 +98,7 @@ constexpr uint32_t kNopRec = 0x00FFu;
 // barrier inside S2.
 struct ModelSmem {
     uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b;
-    int32_t* val; uint16_t* ctx; uint16_t* off; uint32_t* ctot; uint32_t* cmask; uint32_t* misc; uint16_t* stage;
+    int32_t* val; uint16_t* ctx; uint16_t* off; uint32_t* ctot; uint32_t* cmask; uint32_t* misc; uint8_t* tpow; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 constexpr int kMaxChunks = 64;            // wmax <= 2048
@@ -112,9 +112,11 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int first_n
     n += rep ? 64 * 32 * 4 : 256;
     n += align16((size_t)wmax * 4);          // val
     n += align16((size_t)wmax * 2) * 2;      // ctx, off
-    n += kMaxChunks * 4;                     // ctot
-    n += kMaxChunks * kModelWarps * 4;       // cmask
+    const int nch = (wmax + 31) / 32;
+    n += align16((size_t)nch * 4);           // ctot
+    n += (size_t)nch * kModelWarps * 4;      // cmask
     n += 16 * 4;                             // misc
+    n += 5 * 256;                            // tpow
     return n;
 }
 size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int first_n, int stage_cap) {
@@ -131,9 +133,11 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     m.val = reinterpret_cast<int32_t*>(base); base += align16((size_t)wmax * 4);
     m.ctx = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
     m.off = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
-    m.ctot = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * 4;
-    m.cmask = reinterpret_cast<uint32_t*>(base); base += kMaxChunks * kModelWarps * 4;
+    const int nch = (wmax + 31) / 32;
+    m.ctot = reinterpret_cast<uint32_t*>(base); base += align16((size_t)nch * 4);
+    m.cmask = reinterpret_cast<uint32_t*>(base); base += (size_t)nch * kModelWarps * 4;
     m.misc = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
+    m.tpow = base; base += 5 * 256;
     m.stage = reinterpret_cast<uint16_t*>(base);
     return m;
 }
@@ -207,7 +211,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     T1<kRep> t1;
     t1.base = smem_addr(S.t1b) + (kRep ? lane * 4 : 0);
     const uint32_t dummy = smem_addr(S.misc) + lane * 2;    // where the lanes that have no bin in a step put their record
-    const uint32_t stage_a = smem_addr(S.stage), states_a = smem_addr(S.states);
+    const uint32_t stage_a = smem_addr(S.stage), states_a = smem_addr(S.states), tpow_a = smem_addr(S.tpow);
     const uint32_t lt = (1u << lane) - 1u;
 
     const size_t fs = (size_t)frame * A.nslices + slice;
@@ -229,7 +233,8 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
         } else {
             for (int i = tid; i < 256; i += kModelThreads) S.t1b[i] = A.t1q[i];
         }
-        for (int i = tid; i < kMaxChunks * NW; i += kModelThreads) S.cmask[i] = 0;
+        for (int i = tid; i < ((wmax + 31) / 32) * NW; i += kModelThreads) S.cmask[i] = 0;
+        for (int i = tid; i < 5 * 256; i += kModelThreads) S.tpow[i] = A.tpow[i];
     }
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
@@ -447,13 +452,38 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                         // rounds: samples of the batch that share a context go one after the other
                         const uint32_t mm = __match_any_sync(0xffffffffu, cx);
                         const int rank = __popc(mm & lt);
-                        const int maxr = __reduce_max_sync(0xffffffffu, have ? rank : 0);
+                        // runs of zeros: when every sample of the batch that uses a context has residual 0 (flat areas, mattes,
+                        // black frames), the k-th of them sees state one_state^k(st) of slot 0 and nothing else moves: all of
+                        // them at once, through the tables of one_state^(2^i)
+                        bool have2 = have;
+                        {
+                            const bool z = have && v == 0;
+                            const uint32_t mz = __match_any_sync(0xffffffffu, z ? cx : 0x40000u + (uint32_t)lane);
+                            const bool pure = z && mz == mm;
+                            if (__any_sync(0xffffffffu, pure)) {
+                                const uint32_t sa = states_a + (cx & 0xFFFFu) * (uint32_t)kRow;      // slot 0 = byte 0 of the row
+                                uint32_t st = 0;
+                                if (pure) st = lds_u8_volatile(sa);
+                                __syncwarp();
+                                if (pure) {
+                                    const int j = __popc(mz & lt);
+#pragma unroll
+                                    for (int kk = 0; kk < 5; kk++)
+                                        if ((j >> kk) & 1) st = lds_u8(tpow_a + kk * 256 + st);
+                                    sts_u16(stage_a + o * 2u, st + 255u);                             // q = st - 1, bit 1
+                                    if (j == __popc(mz) - 1) sts_u8(sa, lds_u8(tpow_a + st));
+                                }
+                                __syncwarp();
+                                have2 = have && !pure;
+                            }
+                        }
+                        const int maxr = __reduce_max_sync(0xffffffffu, have2 ? rank : 0);
                         const bool nz = v != 0;
                         const uint32_t a = (uint32_t)abs(v);
                         const int e = nz ? 31 - __clz(a) : -1;
                         const bool neg = v < 0;
                         for (int rr = 0; rr <= maxr; rr++) {
-                            const bool act = have && rank == rr;
+                            const bool act = have2 && rank == rr;
                             const uint32_t am = __ballot_sync(0xffffffffu, act);
                             if (__popc(am) >= kDenseMin) {
                                 // ---- one lane per sample, state row in registers

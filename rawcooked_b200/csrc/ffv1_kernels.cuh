@@ -52,6 +52,7 @@ struct EncArgs {
     const SliceGeom* geom;        // [nslices]
     const int16_t* qtab;          // [5][256]
     const uint8_t* t1q;           // [256] t1q[q] = one_state[q + 1]
+    const uint8_t* tpow;          // [5][256] tpow[i][s] = one_state applied 2^i times to state s
     const uint16_t* hdr_bins;     // [nslices][kMaxHeaderBins]  records (q | bit << 8)
     const int32_t* hdr_cnt;       // [nslices]
     const uint32_t* crc_table;    // [256]

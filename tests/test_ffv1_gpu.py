@@ -75,6 +75,28 @@ def test_band_boundaries_and_many_frames():
         enc.close()
 
 
+def test_black_bars_and_black_frames():
+    # runs of zero residuals inside grainy rows (pillarbox / letterbox mattes) and whole black frames: the zero-run path of
+    # k_model (one_state iterated through its power tables) next to the per-sample paths
+    w, h, layout, slices = 400, 120, S.DPX_RGB_16_BE, 4
+    enc = ffv1.FFV1Encoder(w, h, layout, slices=slices, max_frames=3)
+    try:
+        nh, nv = enc.grid
+        g = S.synth_payload(w, h, layout, 77, "grain").reshape(h, w, 6).copy()
+        g[:, : w // 5] = 0
+        g[:, 4 * w // 5:] = 0
+        g[: h // 6] = 0
+        g[h // 2, w // 5: w // 2] = 0x40                 # a constant non-black run inside a row
+        frames = [g.reshape(-1), np.zeros(w * h * 6, dtype=np.uint8), np.full(w * h * 6, 0xFF, dtype=np.uint8)]
+        pkts = enc.encode(frames)
+        for f, p in zip(frames, pkts):
+            assert p == util.oracle_encode(f, w, h, layout, nh, nv)
+            if util.ref_available():
+                assert util.ref_decode(enc.config_record, p, w, h, layout) == f.tobytes()
+    finally:
+        enc.close()
+
+
 def test_config2_frame_2k_10bit():
     # one frame of BASELINE config 2 (2048x1556 10-bit Filled-A BE, -slices 4): wide slices (1024 px)
     w, h, layout = 2048, 1556, S.DPX_RGB_10_FA_BE

@@ -10,6 +10,9 @@ for layout in (S.DPX_RGB_16_BE, S.DPX_RGB_10_FA_BE, S.DPX_RGB_8):
             if layout == S.DPX_RGB_8 and (w * 3) % 4: continue
             cases.append((layout, kind, w, h, sl, 1))
 cases.append((S.DPX_RGB_16_BE, "grain", 96, 64, 4, 0))
+for kind in ("grain", "flat", "const", "white"):
+    cases.append((S.DPX_RGB_8, kind, 640, 480, 16, 1))
+    cases.append((S.DPX_RGB_10_FA_BE, kind, 2048, 160, 4, 1))
 for layout, kind, w, h, sl, ctx in cases:
     try:
         enc = ffv1.FFV1Encoder(w, h, layout, slices=sl, context=ctx, max_frames=2)
