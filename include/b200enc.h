@@ -99,6 +99,12 @@ size_t b200_ffv1_max_packet_bytes(const b200_ffv1_enc* enc);
 int b200_ffv1_encode_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int32_t n_frames,
                           uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len);
 
+/* Asynchronous half of b200_ffv1_encode_host: enqueues the band-by-band host->device copies and the kernels and returns at
+ * once; the frames must stay valid (and should be pinned) until b200_ffv1_packets_device() / b200_ffv1_fetch_packets() has
+ * returned. The caller can then pull the packets it wants from the device arena itself (the front-end streams them one by one
+ * into the Matroska file through a small pinned ring). */
+int b200_ffv1_submit_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int32_t n_frames);
+
 /* Device-resident variant: `d_frames` is ONE device buffer holding n_frames payloads back to back
  * (stride b200_ffv1_frame_bytes()); packets are produced into an internal device buffer.
  * `stream` is a cudaStream_t (0 = default stream); the call is asynchronous on it.

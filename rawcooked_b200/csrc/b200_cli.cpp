@@ -12,12 +12,14 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200enc.h"
@@ -76,6 +78,18 @@ struct AudioStream {
     bool flac = true;
 };
 
+// B200_CLI_TIMING=1: wall-clock of the front-end's phases on stderr
+struct PhaseClock {
+    bool on = getenv("B200_CLI_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "b200enc: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 int fail(const std::string& msg, int code = 1) {
     fprintf(stderr, "b200enc: %s\n", msg.c_str());
     return code;
@@ -88,6 +102,7 @@ int b200_flac_encode_file_to_mux(const std::string& path, const b200::WavInfo& w
                                  std::string* err);   // flac_host.cpp
 
 extern "C" int b200enc_main(int argc, char** argv) {
+    PhaseClock pc;
     std::vector<InputSpec> inputs;
     std::vector<AttachSpec> attaches;
     std::map<std::string, std::string> pending, outopt;
@@ -203,7 +218,9 @@ extern "C" int b200enc_main(int argc, char** argv) {
     std::vector<b200_ffv1_enc*> encs(videos.size(), nullptr);
     std::vector<std::vector<std::pair<int64_t, std::vector<uint8_t>>>> audio_packets(audios.size());
     double duration_ms = 0;
-    int frames_in_flight = 32;
+    // throughput comes from the batch (k_range's serial time per band is fixed) but every frame in flight costs
+    // pinned host memory and device memory that take seconds to set up: 64 is the better trade below a few thousand frames
+    int frames_in_flight = 64;
     if (const char* e = getenv("B200_FRAMES_IN_FLIGHT")) frames_in_flight = std::max(1, atoi(e));
     auto cleanup = [&]() { for (auto* e : encs) b200_ffv1_close(e); };
     for (auto& o : order) {
@@ -254,6 +271,7 @@ extern "C" int b200enc_main(int argc, char** argv) {
         tracks.push_back(std::move(t));
     }
 
+    pc.mark("parse + encoder open");
     b200::MkvWriter mux;
     if (!mux.open(out_path, tracks, atts, duration_ms)) { cleanup(); return fail(mux.error(), B200_ERR_IO); }
 
@@ -272,46 +290,126 @@ extern "C" int b200enc_main(int argc, char** argv) {
         b200_ffv1_enc* E = encs[vi];
         const size_t fb = b200_ffv1_frame_bytes(v.info.width, v.info.height, v.info.layout);
         const size_t B = std::min<size_t>((size_t)frames_in_flight, v.files.size());
-        uint8_t* h_in = nullptr;
-        uint8_t* h_out = nullptr;
-        const size_t out_cap = std::min(b200_ffv1_max_packet_bytes(E), fb * 3 + (1 << 16)) * B;
-        if (cudaHostAlloc((void**)&h_in, fb * B, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc((void**)&h_out, out_cap, cudaHostAllocDefault) != cudaSuccess) {
+        // Source-file ingest at rate: the payloads of a batch are read by `nread` threads (pread straight into pinned
+        // memory, one header parse per file because the payload offset may differ from frame to frame), and the NEXT batch is
+        // read while the GPU encodes the current one (two pinned input buffers).
+        uint8_t* h_in[2] = {nullptr, nullptr};
+        // packets leave the device one by one through a two-slot pinned ring (a packet is tens of MB; pinning a buffer for
+        // a whole batch of worst-case packets would take longer than encoding it)
+        uint8_t* h_ring[2] = {nullptr, nullptr};
+        size_t ring_cap = std::max<size_t>(fb + (fb >> 2), (size_t)1 << 20);
+        cudaStream_t cs = nullptr;
+        cudaEvent_t cev[2] = {nullptr, nullptr};
+        const bool two = v.files.size() > B;
+        // pinning memory is slow (a few GB/s): the second input buffer is pinned in the background while the first batch is
+        // read and encoded
+        bool in1_ok = true;
+        std::thread pin1;
+        if (two) pin1 = std::thread([&] { cudaSetDevice(device); in1_ok = cudaHostAlloc((void**)&h_in[1], fb * B, cudaHostAllocDefault) == cudaSuccess; });
+        if (cudaHostAlloc((void**)&h_in[0], fb * B, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&h_ring[0], ring_cap, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&h_ring[1], ring_cap, cudaHostAllocDefault) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&cev[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&cev[1], cudaEventDisableTiming) != cudaSuccess) {
+            if (pin1.joinable()) pin1.join();
             cleanup(); return fail("cannot allocate pinned host buffers");
         }
+        unsigned nread = std::thread::hardware_concurrency();
+        if (outopt.count("-threads") && atoi(outopt["-threads"].c_str()) > 0) nread = (unsigned)atoi(outopt["-threads"].c_str());
+        nread = std::max(1u, std::min(nread, 32u));
+        // reads frames [f0, f0 + n) into dst; returns "" or the first error
+        auto read_batch = [&](size_t f0, size_t n, uint8_t* dst) -> std::string {
+            std::vector<std::string> errs(nread);
+            auto work = [&](unsigned t) {
+                for (size_t k = t; k < n && errs[t].empty(); k += nread) {
+                    const std::string& path = v.files[f0 + k];
+                    const int fd = open(path.c_str(), O_RDONLY);
+                    if (fd < 0) { errs[t] = "cannot open " + path; return; }
+                    b200::ImageInfo fi = v.info;
+                    if (f0 + k > 0) {
+                        std::vector<uint8_t> head(65536);
+                        const ssize_t hn = pread(fd, head.data(), head.size(), 0);
+                        std::string err;
+                        const bool ok = v.kind == 'd' ? b200::parse_dpx(head.data(), hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &err)
+                                                      : b200::parse_tiff(head.data(), hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &err);
+                        if (!ok || fi.width != v.info.width || fi.height != v.info.height || fi.layout != v.info.layout) {
+                            close(fd);
+                            errs[t] = path + ": " + (ok ? std::string("geometry differs from the first frame") : err);
+                            return;
+                        }
+                    }
+                    if (!read_at(fd, dst + k * fb, fb, fi.data_offset)) { close(fd); errs[t] = "cannot read " + path; return; }
+                    close(fd);
+                }
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nread; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto& x : th) x.join();
+            for (auto& e : errs) if (!e.empty()) return e;
+            return "";
+        };
         std::vector<const uint8_t*> ptrs(B);
         std::vector<size_t> off(B), len(B);
+        pc.mark("pinned buffers");
+        std::string rerr = read_batch(0, std::min(B, v.files.size()), h_in[0]);
+        pc.mark("first batch read");
+        if (!rerr.empty()) { cleanup(); return fail(rerr, B200_ERR_IO); }
+        int cur = 0;
         for (size_t f0 = 0; f0 < v.files.size(); f0 += B) {
             const size_t n = std::min(B, v.files.size() - f0);
-            for (size_t k = 0; k < n; k++) {
-                const std::string& path = v.files[f0 + k];
-                const int fd = open(path.c_str(), O_RDONLY);
-                if (fd < 0) { cleanup(); return fail("cannot open " + path, B200_ERR_IO); }
-                b200::ImageInfo fi = v.info;
-                if (f0 + k > 0) {   // header of every file: the payload offset may differ from frame to frame
-                    uint8_t head[65536];
-                    const ssize_t hn = pread(fd, head, sizeof head, 0);
-                    std::string err;
-                    const bool ok = v.kind == 'd' ? b200::parse_dpx(head, hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &err)
-                                                  : b200::parse_tiff(head, hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &err);
-                    if (!ok || fi.width != v.info.width || fi.height != v.info.height || fi.layout != v.info.layout) {
-                        close(fd); cleanup(); return fail(path + ": " + (ok ? std::string("geometry differs from the first frame") : err));
-                    }
+            std::string next_err;
+            std::thread prefetch;
+            if (pin1.joinable()) { pin1.join(); if (!in1_ok) { cleanup(); return fail("cannot allocate pinned host buffers"); } }
+            if (f0 + B < v.files.size())
+                prefetch = std::thread([&, f0] { next_err = read_batch(f0 + B, std::min(B, v.files.size() - f0 - B), h_in[cur ^ 1]); });
+            for (size_t k = 0; k < n; k++) ptrs[k] = h_in[cur] + k * fb;
+            int rc = b200_ffv1_submit_host(E, ptrs.data(), (int32_t)n);
+            const void* d_arena = nullptr;
+            if (!rc) rc = b200_ffv1_packets_device(E, &d_arena, off.data(), len.data(), (int32_t)n);   // waits for the encode
+            pc.mark("encode (batch)");
+            bool mux_ok = rc == 0;
+            // packet k+1 crosses PCIe while packet k is written to the file
+            auto fetch = [&](size_t k) -> bool {
+                const int sl = (int)(k & 1);
+                if (len[k] > ring_cap) {                       // a packet larger than 1.25 x the frame: grow the ring
+                    cudaStreamSynchronize(cs);
+                    cudaFreeHost(h_ring[0]); cudaFreeHost(h_ring[1]);
+                    ring_cap = len[k] + (len[k] >> 3);
+                    if (cudaHostAlloc((void**)&h_ring[0], ring_cap, cudaHostAllocDefault) != cudaSuccess ||
+                        cudaHostAlloc((void**)&h_ring[1], ring_cap, cudaHostAllocDefault) != cudaSuccess) return false;
                 }
-                if (!read_at(fd, h_in + k * fb, fb, fi.data_offset)) { close(fd); cleanup(); return fail("cannot read " + path, B200_ERR_IO); }
-                close(fd);
-                ptrs[k] = h_in + k * fb;
-            }
-            const int rc = b200_ffv1_encode_host(E, ptrs.data(), (int32_t)n, h_out, out_cap, off.data(), len.data());
-            if (rc) { cleanup(); return fail(std::string("ffv1 encode: ") + b200_last_error()); }
-            for (size_t k = 0; k < n; k++) {
+                return cudaMemcpyAsync(h_ring[sl], static_cast<const uint8_t*>(d_arena) + off[k], len[k], cudaMemcpyDeviceToHost, cs) == cudaSuccess &&
+                       cudaEventRecord(cev[sl], cs) == cudaSuccess;
+            };
+            if (mux_ok) mux_ok = fetch(0);
+            for (size_t k = 0; k < n && mux_ok; k++) {
+                if (cudaEventSynchronize(cev[k & 1]) != cudaSuccess) { mux_ok = false; break; }
+                // the ring may only be re-used (or re-allocated) once the block that lives in it has been written
                 const int64_t t_ms = (int64_t)std::llround(1000.0 * (double)(f0 + k) / v.fps);
-                if (!flush_audio_until(t_ms) || !mux.write_block(v.track, t_ms, h_out + off[k], len[k])) { cleanup(); return fail(mux.error(), B200_ERR_IO); }
+                if (k + 1 < n && len[k + 1] <= ring_cap && !fetch(k + 1)) { mux_ok = false; break; }
+                mux_ok = flush_audio_until(t_ms) && mux.write_block(v.track, t_ms, h_ring[k & 1], len[k]);
+                if (mux_ok && k + 1 < n && len[k + 1] > ring_cap) mux_ok = fetch(k + 1);
             }
+            pc.mark("mux write (batch)");
+            if (prefetch.joinable()) prefetch.join();
+            pc.mark("wait for next batch read");
+            if (rc) { cleanup(); return fail(std::string("ffv1 encode: ") + b200_last_error()); }
+            if (!mux_ok) { cleanup(); return fail(mux.error(), B200_ERR_IO); }
+            if (!next_err.empty()) { cleanup(); return fail(next_err, B200_ERR_IO); }
+            cur ^= 1;
         }
-        cudaFreeHost(h_in);
-        cudaFreeHost(h_out);
+        cudaStreamSynchronize(cs);
+        cudaFreeHost(h_in[0]);
+        if (h_in[1]) cudaFreeHost(h_in[1]);
+        cudaFreeHost(h_ring[0]); cudaFreeHost(h_ring[1]);
+        cudaEventDestroy(cev[0]); cudaEventDestroy(cev[1]);
+        cudaStreamDestroy(cs);
     }
     if (!flush_audio_until(INT64_MAX) || !mux.close()) { cleanup(); return fail(mux.error(), B200_ERR_IO); }
+    pc.mark("mux close");
     cleanup();
+    pc.mark("encoder close");
     return 0;
 }

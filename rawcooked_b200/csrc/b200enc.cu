@@ -462,16 +462,21 @@ int b200_ffv1_fetch_packets(b200_ffv1_enc* E, uint8_t* out, size_t out_cap, size
     return 0;
 }
 
-int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames,
-                          uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len) {
-    if (!E || !frames || !out) return fail(B200_ERR_INVALID, "null argument");
+int b200_ffv1_submit_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames) {
+    if (!E || !frames) return fail(B200_ERR_INVALID, "null argument");
     if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
     CU(cudaSetDevice(E->cfg.device));
     const size_t fb = E->st.frame_bytes;
     if (!E->d_in) CU(cudaMalloc((void**)&E->d_in, fb * E->max_frames));
     for (int i = 0; i < n_frames; i++)
         if (!frames[i]) return fail(B200_ERR_INVALID, "null frame pointer");
-    int r = encode_impl(E, E->d_in, n_frames, nullptr, frames);
+    return encode_impl(E, E->d_in, n_frames, nullptr, frames);
+}
+
+int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames,
+                          uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len) {
+    if (!out) return fail(B200_ERR_INVALID, "null argument");
+    int r = b200_ffv1_submit_host(E, frames, n_frames);
     if (r) return r;
     CU(cudaStreamSynchronize(0));
     return b200_ffv1_fetch_packets(E, out, out_cap, out_off, out_len, n_frames);

@@ -101,7 +101,6 @@ struct ModelSmem {
     int32_t* val; uint16_t* ctx; uint16_t* off; uint32_t* ctot; uint32_t* cmask; uint32_t* misc; uint8_t* tpow; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-constexpr int kMaxChunks = 64;            // wmax <= 2048
 
 // bytes of everything except the record staging area. first_n > 0: t1 replicated per bank.
 size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int first_n) {

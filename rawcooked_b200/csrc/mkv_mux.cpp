@@ -1,5 +1,8 @@
 #include "mkv_mux.h"
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cstring>
 
 namespace b200 {
@@ -51,18 +54,51 @@ void el_master(std::vector<uint8_t>& o, uint32_t id, const std::vector<uint8_t>&
 
 }  // namespace
 
-MkvWriter::~MkvWriter() { if (f_) fclose(f_); }
+MkvWriter::~MkvWriter() { if (fd_ >= 0) ::close(fd_); }
+
+// Packets are tens of megabytes: they go straight from the caller's buffer to write(2); only the small pieces (element
+// headers) are gathered in a buffer. Sizes that are not known when an element starts (Segment, Cluster) are written as
+// 8-byte placeholders and patched with pwrite once the element is complete.
+bool MkvWriter::flush_small() {
+    size_t done = 0;
+    while (done < small_.size()) {
+        const ssize_t r = ::write(fd_, small_.data() + done, small_.size() - done);
+        if (r <= 0) { err_ = "write failed"; return false; }
+        done += (size_t)r;
+    }
+    small_.clear();
+    return true;
+}
 
 bool MkvWriter::put(const void* p, size_t n) {
-    if (n && fwrite(p, 1, n, f_) != n) { err_ = "write failed"; return false; }
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    if (n < (256u << 10)) {
+        small_.insert(small_.end(), b, b + n);
+        if (small_.size() > (4u << 20) && !flush_small()) return false;
+    } else {
+        if (!flush_small()) return false;
+        size_t done = 0;
+        while (done < n) {
+            const ssize_t r = ::write(fd_, b + done, n - done);
+            if (r <= 0) { err_ = "write failed"; return false; }
+            done += (size_t)r;
+        }
+    }
     pos_ += n;
     return true;
 }
 
+bool MkvWriter::patch_size8(uint64_t at, uint64_t value) {
+    if (!flush_small()) return false;
+    std::vector<uint8_t> sz;
+    put_size8(sz, value);
+    if (::pwrite(fd_, sz.data(), 8, (off_t)at) != 8) { err_ = "cannot patch an element size"; return false; }
+    return true;
+}
+
 bool MkvWriter::open(const std::string& path, const std::vector<MkvTrack>& tracks, const std::vector<MkvAttachment>& atts, double duration_ms) {
-    f_ = fopen(path.c_str(), "wb");
-    if (!f_) { err_ = "cannot create " + path; return false; }
-    setvbuf(f_, nullptr, _IOFBF, 8 << 20);
+    fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd_ < 0) { err_ = "cannot create " + path; return false; }
     std::vector<uint8_t> h, body;
     el_uint(body, 0x4286, 1); el_uint(body, 0x42F7, 1); el_uint(body, 0x42F2, 4); el_uint(body, 0x42F3, 8);
     el_str(body, 0x4282, "matroska"); el_uint(body, 0x4287, 4); el_uint(body, 0x4285, 2);
@@ -130,13 +166,7 @@ bool MkvWriter::open(const std::string& path, const std::vector<MkvTrack>& track
 
 bool MkvWriter::flush_cluster() {
     if (cluster_time_ < 0) return true;
-    std::vector<uint8_t> h, ts;
-    el_uint(ts, 0xE7, (uint64_t)cluster_time_);
-    put_id(h, 0x1F43B675);
-    put_size(h, ts.size() + cluster_.size());
-    h.insert(h.end(), ts.begin(), ts.end());
-    bool ok = put(h.data(), h.size()) && put(cluster_.data(), cluster_.size());
-    cluster_.clear();
+    const bool ok = patch_size8(cluster_size_at_, pos_ - cluster_data_start_);
     cluster_time_ = -1;
     return ok;
 }
@@ -144,29 +174,33 @@ bool MkvWriter::flush_cluster() {
 bool MkvWriter::write_block(int track, int64_t time_ms, const uint8_t* data, size_t len, bool keyframe) {
     if (track < 1 || track > 126) { err_ = "bad track number"; return false; }
     // new Cluster at most every 5 s / 32 MiB, and always before the 16-bit relative timestamp would overflow
-    if (cluster_time_ >= 0 && (time_ms - cluster_time_ > 5000 || time_ms < cluster_time_ || cluster_.size() > (32u << 20)))
+    if (cluster_time_ >= 0 && (time_ms - cluster_time_ > 5000 || time_ms < cluster_time_ || pos_ - cluster_data_start_ > (32u << 20)))
         if (!flush_cluster()) return false;
-    if (cluster_time_ < 0) cluster_time_ = time_ms;
+    std::vector<uint8_t> h;
+    if (cluster_time_ < 0) {
+        cluster_time_ = time_ms;
+        put_id(h, 0x1F43B675);
+        cluster_size_at_ = pos_ + h.size();
+        put_size8(h, 0);
+        cluster_data_start_ = pos_ + h.size();
+        el_uint(h, 0xE7, (uint64_t)cluster_time_);
+    }
     const int64_t rel = time_ms - cluster_time_;
-    put_id(cluster_, 0xA3);
-    put_size(cluster_, len + 4);
-    cluster_.push_back((uint8_t)(0x80 | track));
-    cluster_.push_back((uint8_t)(rel >> 8));
-    cluster_.push_back((uint8_t)rel);
-    cluster_.push_back(keyframe ? 0x80 : 0x00);
-    cluster_.insert(cluster_.end(), data, data + len);
-    return true;
+    put_id(h, 0xA3);
+    put_size(h, len + 4);
+    h.push_back((uint8_t)(0x80 | track));
+    h.push_back((uint8_t)(rel >> 8));
+    h.push_back((uint8_t)rel);
+    h.push_back(keyframe ? 0x80 : 0x00);
+    return put(h.data(), h.size()) && put(data, len);
 }
 
 bool MkvWriter::close() {
-    if (!f_) return true;
+    if (fd_ < 0) return true;
     bool ok = flush_cluster();
-    const uint64_t seg_size = pos_ - segment_data_start_;
-    std::vector<uint8_t> sz;
-    put_size8(sz, seg_size);
-    if (ok && (fseek(f_, (long)(segment_data_start_ - 8), SEEK_SET) != 0 || fwrite(sz.data(), 1, 8, f_) != 8)) { err_ = "cannot patch Segment size"; ok = false; }
-    if (fclose(f_) != 0 && ok) { err_ = "close failed"; ok = false; }
-    f_ = nullptr;
+    ok = ok && patch_size8(segment_data_start_ - 8, pos_ - segment_data_start_);
+    if (::close(fd_) != 0 && ok) { err_ = "close failed"; ok = false; }
+    fd_ = -1;
     return ok;
 }
 

@@ -37,11 +37,14 @@ class MkvWriter {
 
   private:
     bool put(const void* p, size_t n);
+    bool flush_small();
+    bool patch_size8(uint64_t at, uint64_t value);
     bool flush_cluster();
-    FILE* f_ = nullptr;
+    int fd_ = -1;
     std::string err_;
     uint64_t pos_ = 0, segment_size_pos_ = 0, segment_data_start_ = 0;
-    std::vector<uint8_t> cluster_;        // blocks of the open cluster
+    std::vector<uint8_t> small_;          // element headers not yet written
+    uint64_t cluster_size_at_ = 0, cluster_data_start_ = 0;   // file offsets of the open Cluster's size field / first child
     int64_t cluster_time_ = -1;
 };
 
