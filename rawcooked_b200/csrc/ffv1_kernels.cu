@@ -114,7 +114,7 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int first_n
     const int nch = (wmax + 31) / 32;
     n += align16((size_t)nch * 4);           // ctot
     n += (size_t)nch * kModelWarps * 4;      // cmask
-    n += 16 * 4;                             // misc
+    n += kModelWarps * 64;                   // misc: per-lane landing place of the records of idle lanes
     n += 5 * 256;                            // tpow
     return n;
 }
@@ -135,7 +135,7 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     const int nch = (wmax + 31) / 32;
     m.ctot = reinterpret_cast<uint32_t*>(base); base += align16((size_t)nch * 4);
     m.cmask = reinterpret_cast<uint32_t*>(base); base += (size_t)nch * kModelWarps * 4;
-    m.misc = reinterpret_cast<uint32_t*>(base); base += 16 * 4;
+    m.misc = reinterpret_cast<uint32_t*>(base); base += kModelWarps * 64;
     m.tpow = base; base += 5 * 256;
     m.stage = reinterpret_cast<uint16_t*>(base);
     return m;
@@ -209,7 +209,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
     T1<kRep> t1;
     t1.base = smem_addr(S.t1b) + (kRep ? lane * 4 : 0);
-    const uint32_t dummy = smem_addr(S.misc) + lane * 2;    // where the lanes that have no bin in a step put their record
+    const uint32_t dummy = smem_addr(S.misc) + warp * 64 + lane * 2;   // where the lanes that have no bin in a step put their record
     const uint32_t stage_a = smem_addr(S.stage), states_a = smem_addr(S.states), tpow_a = smem_addr(S.tpow);
     const uint32_t lt = (1u << lane) - 1u;
 
