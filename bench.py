@@ -283,16 +283,22 @@ def run_b200(args):
     offs = (C.c_size_t * F)()
     lens = (C.c_size_t * F)()
 
-    def step_e2e():
-        rc = L.b200_ffv1_encode_host(enc._h, ptrs, F, out_np.ctypes.data, out_np.size, offs, lens)
+    def ck(rc):
         if rc:
             raise RuntimeError(L.b200_last_error().decode())
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+
+    def run_e2e(steps):
+        """`steps` batches through the host entry points, two in flight: batch i+1 is submitted (H2D band by band + kernels)
+        before the packets of batch i are fetched (D2H), so both PCIe directions hide behind the kernels."""
+        ck(L.b200_ffv1_submit_host(enc._h, ptrs, F))
+        for _ in range(steps - 1):
+            ck(L.b200_ffv1_submit_host(enc._h, ptrs, F))
+            ck(L.b200_ffv1_fetch_packets(enc._h, out_np.ctypes.data, out_np.size, offs, lens, F))
+        ck(L.b200_ffv1_fetch_packets(enc._h, out_np.ctypes.data, out_np.size, offs, lens, F))
+    run_e2e(max(2, args.warmup // 2))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -339,7 +345,7 @@ def run_b200(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload_config(F, world),
             "e2e": {"value": e2e, "unit": "MPix/s", "h2d_bytes_per_step": F * fb * world, "d2h_bytes_per_step": int(out_bytes) * world,
-                    "api": "b200_ffv1_encode_host (pinned host frames -> packets in pinned host memory; H2D band by band behind the kernels)", "fps": e2e * 1e6 / (W * H)},
+                    "api": "b200_ffv1_submit_host + b200_ffv1_fetch_packets, two batches in flight (pinned host frames -> packets in pinned host memory; every step's frames cross PCIe inside the timed region, H2D band by band, D2H of batch i during batch i+1)", "fps": e2e * 1e6 / (W * H)},
             "gpu_launches": int(st["launches"]) * args.steps * world,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,

@@ -100,9 +100,12 @@ int b200_ffv1_encode_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int3
                           uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len);
 
 /* Asynchronous half of b200_ffv1_encode_host: enqueues the band-by-band host->device copies and the kernels and returns at
- * once; the frames must stay valid (and should be pinned) until b200_ffv1_packets_device() / b200_ffv1_fetch_packets() has
- * returned. The caller can then pull the packets it wants from the device arena itself (the front-end streams them one by one
- * into the Matroska file through a small pinned ring). */
+ * once; the frames must stay valid (and should be pinned) until the batch has been collected. Up to TWO batches may be in
+ * flight: b200_ffv1_fetch_packets() / b200_ffv1_packets_device() always collect the OLDEST one, so
+ *     submit(0); submit(1); fetch -> 0; submit(2); fetch -> 1; ...
+ * moves the packets of batch i over PCIe while batch i+1 is being coded (two result sets on the device; the second one is
+ * allocated when first needed). A third submit without a fetch gives up the oldest batch. Do not mix with
+ * b200_ffv1_encode_device while host batches are in flight. */
 int b200_ffv1_submit_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int32_t n_frames);
 
 /* Device-resident variant: `d_frames` is ONE device buffer holding n_frames payloads back to back

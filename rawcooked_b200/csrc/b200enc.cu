@@ -56,9 +56,23 @@ struct b200_ffv1_enc {
     bool trace_pending = false;
     bool timed_pending = false;
     uint64_t stats[8] = {0};
-    int last_frames = 0;
-    std::vector<uint64_t> h_off, h_len;
-    uint32_t* h_flags = nullptr;    // pinned mirror of flags
+    // Results of an encode call (packet arena, slice / frame tables, flags). Two sets: while the packets of one batch
+    // cross PCIe, the next batch submitted with b200_ffv1_submit_host is already coding into the other set. Set 1 is
+    // allocated the first time two host batches are in flight; the device entry point always uses set 0.
+    struct ResultSet {
+        uint8_t* arena = nullptr;
+        uint32_t* slice_size = nullptr;
+        uint64_t *slice_off = nullptr, *frame_off = nullptr, *frame_len = nullptr;
+        uint32_t* flags = nullptr;
+        uint32_t* h_flags = nullptr;    // pinned mirror of flags
+        std::vector<uint64_t> h_off, h_len;
+        cudaEvent_t done = nullptr;
+        int n_frames = 0;
+    } rs[2];
+    int fifo[2] = {0, 0};           // result sets submitted and not yet collected, oldest first
+    int fifo_n = 0;
+    bool host_mode = false;         // batches come from b200_ffv1_submit_host (queue semantics) / from b200_ffv1_encode_device (the last call stays collectable)
+    cudaStream_t sh = nullptr, sf = nullptr;   // stream of the host entry points / of the device-to-host fetches
 };
 
 extern "C" {
@@ -248,10 +262,21 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     for (cudaEvent_t* ev : {&E->ev_start, &E->ev_done_m, &E->ev_done_e}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     for (int pz = 0; pz < b200_ffv1_enc::kPar; pz++)
         for (cudaEvent_t* ev : {&E->ev_model[pz], &E->ev_range[pz], &E->ev_emit[pz]}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
-    cudaError_t e2 = cudaHostAlloc((void**)&E->h_flags, 256, cudaHostAllocDefault);
+    {
+        b200_ffv1_enc::ResultSet& R = E->rs[0];
+        R.arena = A.arena; R.slice_size = A.slice_size; R.slice_off = A.slice_off; R.frame_off = A.frame_off; R.frame_len = A.frame_len;
+        R.flags = A.flags;
+    }
+    cudaError_t e2 = cudaSuccess;
+    for (auto& R : E->rs) {
+        if (e2 == cudaSuccess) e2 = cudaHostAlloc((void**)&R.h_flags, 256, cudaHostAllocDefault);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&R.done, cudaEventDisableTiming);
+        R.h_off.resize(B); R.h_len.resize(B);
+    }
     if (e2 != cudaSuccess) { int rc = fail_cuda(e2, "cudaHostAlloc"); b200_ffv1_close(E); return rc; }
+    cudaStreamCreateWithFlags(&E->sh, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&E->sf, cudaStreamNonBlocking);
     for (auto& ev : E->ev) cudaEventCreate(&ev);
-    E->h_off.resize(B); E->h_len.resize(B);
     e2 = cudaDeviceSynchronize();
     if (e2 != cudaSuccess) { int rc = fail_cuda(e2, "init"); b200_ffv1_close(E); return rc; }
     *out = E;
@@ -264,7 +289,16 @@ void b200_ffv1_close(b200_ffv1_enc* E) {
     cudaDeviceSynchronize();
     for (void* p : E->owned) cudaFree(p);
     if (E->d_in) cudaFree(E->d_in);
-    if (E->h_flags) cudaFreeHost(E->h_flags);
+    for (auto& R : E->rs) {
+        if (R.h_flags) cudaFreeHost(R.h_flags);
+        if (R.done) cudaEventDestroy(R.done);
+    }
+    {   // set 1 is allocated outside `owned`
+        b200_ffv1_enc::ResultSet& R = E->rs[1];
+        for (void* q : {(void*)R.arena, (void*)R.slice_size, (void*)R.slice_off, (void*)R.frame_off, (void*)R.frame_len, (void*)R.flags})
+            if (q) cudaFree(q);
+    }
+    for (cudaStream_t st : {E->sh, E->sf}) if (st) cudaStreamDestroy(st);
     for (auto& ev : E->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : E->tev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : {E->ev_start, E->ev_done_m, E->ev_done_e}) if (ev) cudaEventDestroy(ev);
@@ -292,13 +326,28 @@ int b200_ffv1_set_timing(b200_ffv1_enc* E, int32_t enabled) {
 
 // host_frames != nullptr: the payloads are still in host memory; they are copied to d_frames band by band on the copy stream,
 // each band's rows just ahead of the k_model launch that needs them, so that the transfer hides behind the kernels
-static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, cudaStream_t s, const uint8_t* const* host_frames) {
+static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, cudaStream_t s, const uint8_t* const* host_frames, int set) {
     CU(cudaSetDevice(E->cfg.device));
+    b200_ffv1_enc::ResultSet& R = E->rs[set];
+    if (!R.arena) {     // second result set, first use
+        const b200::EncArgs& A0 = E->args;
+        const size_t B = (size_t)E->max_frames, ns = (size_t)A0.nslices;
+        CU(cudaMalloc((void**)&R.arena, A0.arena_cap));
+        CU(cudaMalloc((void**)&R.slice_size, B * ns * 4));
+        CU(cudaMalloc((void**)&R.slice_off, B * ns * 8));
+        CU(cudaMalloc((void**)&R.frame_off, B * 8));
+        CU(cudaMalloc((void**)&R.frame_len, B * 8));
+        CU(cudaMalloc((void**)&R.flags, 256));
+    }
     constexpr int kPar = b200_ffv1_enc::kPar;
     b200::EncArgs A[kPar];
     A[0] = E->args;
     for (int pz = 1; pz < kPar; pz++) A[pz] = E->argsN[pz];
-    for (int pz = 0; pz < kPar; pz++) A[pz].in = static_cast<const uint8_t*>(d_frames);
+    for (int pz = 0; pz < kPar; pz++) {
+        A[pz].in = static_cast<const uint8_t*>(d_frames);
+        A[pz].arena = R.arena; A[pz].slice_size = R.slice_size; A[pz].slice_off = R.slice_off; A[pz].frame_off = R.frame_off;
+        A[pz].frame_len = R.frame_len; A[pz].flags = R.flags;
+    }
     CU(cudaMemsetAsync(A[0].flags, 0, 256, s));
     CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)n_frames * A[0].nslices * A[0].slice_cap, s));   // k_emit accumulates into it
     // Three kernels per band on three streams: model(b) -> range(b) -> emit(b); model(b) reuses the band buffers of
@@ -379,7 +428,8 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
     if (tm) CU(cudaEventRecord(E->tev[(size_t)nb * 4 + 1], s));
     E->timed_pending = tm;
     launches += 2;
-    E->last_frames = n_frames;
+    R.n_frames = n_frames;
+    CU(cudaEventRecord(R.done, s));
     E->stats[0] = launches;
     E->stats[2] = (uint64_t)n_frames * E->st.width * E->st.height * 3;
     return 0;
@@ -388,15 +438,26 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
 int b200_ffv1_encode_device(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, void* stream) {
     if (!E || !d_frames) return fail(B200_ERR_INVALID, "null argument");
     if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
-    return encode_impl(E, d_frames, n_frames, static_cast<cudaStream_t>(stream), nullptr);
+    E->fifo[0] = 0; E->fifo_n = 1; E->host_mode = false;   // the device entry point has one result set: the last call's
+    return encode_impl(E, d_frames, n_frames, static_cast<cudaStream_t>(stream), nullptr, 0);
 }
 
-static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* out_len, uint64_t* total) {
-    if (n_frames != E->last_frames) return fail(B200_ERR_INVALID, "n_frames differs from the last encode call");
+// waits for the oldest batch in flight and reads its tables; the batch stays at the head of the queue until `pop`
+static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* out_len, uint64_t* total, bool pop, int* which) {
+    if (E->fifo_n == 0) return fail(B200_ERR_INVALID, "no encode call to collect");
+    const int set = E->fifo[0];
+    b200_ffv1_enc::ResultSet& R = E->rs[set];
+    if (which) *which = set;
+    if (n_frames != R.n_frames) return fail(B200_ERR_INVALID, "n_frames differs from the encode call being collected");
+    if (pop && E->host_mode) { E->fifo[0] = E->fifo[1]; E->fifo_n--; }
     const b200::EncArgs& A = E->args;
-    CU(cudaMemcpy(E->h_flags, A.flags, 256, cudaMemcpyDeviceToHost));
+    CU(cudaEventSynchronize(R.done));
+    CU(cudaMemcpyAsync(R.h_flags, R.flags, 256, cudaMemcpyDeviceToHost, E->sf));
+    CU(cudaMemcpyAsync(R.h_off.data(), R.frame_off, (size_t)n_frames * 8, cudaMemcpyDeviceToHost, E->sf));
+    CU(cudaMemcpyAsync(R.h_len.data(), R.frame_len, (size_t)n_frames * 8, cudaMemcpyDeviceToHost, E->sf));
+    CU(cudaStreamSynchronize(E->sf));
     if (getenv("B200_PHASE_TIMING")) {
-        const unsigned long long* ph = reinterpret_cast<const unsigned long long*>(E->h_flags + 16);
+        const unsigned long long* ph = reinterpret_cast<const unsigned long long*>(R.h_flags + 16);
         fprintf(stderr, "k_model phase cycles (sum over CTAs): S1 %llu S2p %llu S2a %llu S2b %llu S3 %llu\n", ph[0], ph[1], ph[2], ph[3], ph[4]);
     }
     if (E->trace_pending) {
@@ -410,18 +471,16 @@ static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* 
         }
         E->trace_pending = false;
     }
-    if (E->h_flags[0] & 1u) return fail(B200_ERR_OVERFLOW, "slice scratch overflow");
-    if (E->h_flags[0] & 2u) return fail(B200_ERR_OVERFLOW, "packet arena overflow");
-    if (E->h_flags[0] & 4u) return fail(B200_ERR_OVERFLOW, "plane-row needs more column segments than reserved");
-    CU(cudaMemcpy(E->h_off.data(), A.frame_off, (size_t)n_frames * 8, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(E->h_len.data(), A.frame_len, (size_t)n_frames * 8, cudaMemcpyDeviceToHost));
+    if (R.h_flags[0] & 1u) return fail(B200_ERR_OVERFLOW, "slice scratch overflow");
+    if (R.h_flags[0] & 2u) return fail(B200_ERR_OVERFLOW, "packet arena overflow");
+    if (R.h_flags[0] & 4u) return fail(B200_ERR_OVERFLOW, "plane-row needs more column segments than reserved");
     uint64_t tot = 0;
     for (int i = 0; i < n_frames; i++) {
-        if (out_off) out_off[i] = (size_t)E->h_off[i];
-        if (out_len) out_len[i] = (size_t)E->h_len[i];
-        tot += E->h_len[i];
+        if (out_off) out_off[i] = (size_t)R.h_off[i];
+        if (out_len) out_len[i] = (size_t)R.h_len[i];
+        tot += R.h_len[i];
     }
-    E->stats[1] = (uint64_t)E->h_flags[2] | ((uint64_t)E->h_flags[3] << 32);
+    E->stats[1] = (uint64_t)R.h_flags[2] | ((uint64_t)R.h_flags[3] << 32);
     if (E->timed_pending) {      // device time of each kernel class in the last (serial, timed) encode, microseconds
         double tmod = 0, trng = 0, temt = 0, tpk = 0;
         float ms = 0;
@@ -445,9 +504,12 @@ static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* 
 int b200_ffv1_packets_device(b200_ffv1_enc* E, const void** d_arena, size_t* out_off, size_t* out_len, int32_t n_frames) {
     if (!E) return fail(B200_ERR_INVALID, "null encoder");
     CU(cudaSetDevice(E->cfg.device));
-    int r = collect(E, n_frames, out_off, out_len, nullptr);
+    // the batch leaves the queue: the caller reads its arena before submitting again (with two batches in flight the arena
+    // returned here is the one the NEXT submit will not touch)
+    int set = 0;
+    int r = collect(E, n_frames, out_off, out_len, nullptr, true, &set);
     if (r) return r;
-    if (d_arena) *d_arena = E->args.arena;
+    if (d_arena) *d_arena = E->rs[set].arena;
     return 0;
 }
 
@@ -455,10 +517,12 @@ int b200_ffv1_fetch_packets(b200_ffv1_enc* E, uint8_t* out, size_t out_cap, size
     if (!E || !out) return fail(B200_ERR_INVALID, "null argument");
     CU(cudaSetDevice(E->cfg.device));
     uint64_t total = 0;
-    int r = collect(E, n_frames, out_off, out_len, &total);
+    int set = 0;
+    int r = collect(E, n_frames, out_off, out_len, &total, true, &set);
     if (r) return r;
     if (total > out_cap) return fail(B200_ERR_OVERFLOW, "output buffer too small");
-    CU(cudaMemcpy(out, E->args.arena, (size_t)total, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(out, E->rs[set].arena, (size_t)total, cudaMemcpyDeviceToHost, E->sf));
+    CU(cudaStreamSynchronize(E->sf));
     return 0;
 }
 
@@ -470,7 +534,13 @@ int b200_ffv1_submit_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_
     if (!E->d_in) CU(cudaMalloc((void**)&E->d_in, fb * E->max_frames));
     for (int i = 0; i < n_frames; i++)
         if (!frames[i]) return fail(B200_ERR_INVALID, "null frame pointer");
-    return encode_impl(E, E->d_in, n_frames, nullptr, frames);
+    // result set: 0 when nothing is in flight; the free one when one batch is; with two in flight the oldest is given up
+    if (!E->host_mode) { E->fifo_n = 0; E->host_mode = true; }
+    int set = 0;
+    if (E->fifo_n == 1) set = E->fifo[0] ^ 1;
+    else if (E->fifo_n == 2) { set = E->fifo[0]; E->fifo[0] = E->fifo[1]; E->fifo_n = 1; }
+    E->fifo[E->fifo_n++] = set;
+    return encode_impl(E, E->d_in, n_frames, E->sh, frames, set);
 }
 
 int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames,
@@ -478,7 +548,6 @@ int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_
     if (!out) return fail(B200_ERR_INVALID, "null argument");
     int r = b200_ffv1_submit_host(E, frames, n_frames);
     if (r) return r;
-    CU(cudaStreamSynchronize(0));
     return b200_ffv1_fetch_packets(E, out, out_cap, out_off, out_len, n_frames);
 }
 

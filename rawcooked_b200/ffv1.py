@@ -46,6 +46,7 @@ def load_library():
     L.b200_ffv1_max_packet_bytes.argtypes = [C.c_void_p]
     L.b200_ffv1_encode_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t,
                                         C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.b200_ffv1_submit_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
     L.b200_ffv1_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.b200_ffv1_packets_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32]
     L.b200_ffv1_fetch_packets.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32]
@@ -121,6 +122,18 @@ class FFV1Encoder:
         ln = (C.c_size_t * n)()
         _check(self._L.b200_ffv1_encode_host(self._h, ptrs, n, out.ctypes.data, cap, off, ln))
         return [out[off[i]:off[i] + ln[i]].tobytes() for i in range(n)]
+
+    def submit(self, frames):
+        """Asynchronous host entry point: enqueues the batch (host->device copies band by band + kernels) and returns; up to
+        two batches may be in flight, `fetch_packets` always collects the oldest. The arrays are kept alive until then."""
+        n = len(frames)
+        arrs = [np.ascontiguousarray(np.frombuffer(f, np.uint8) if not isinstance(f, np.ndarray) else f, dtype=np.uint8) for f in frames]
+        for a in arrs:
+            if a.size != self.frame_bytes:
+                raise ValueError("frame has %d bytes, layout needs %d" % (a.size, self.frame_bytes))
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        self._inflight = getattr(self, "_inflight", [])[-1:] + [(arrs, ptrs)]
+        _check(self._L.b200_ffv1_submit_host(self._h, ptrs, n))
 
     def encode_device(self, d_ptr, n_frames, stream=0):
         """Asynchronous device-resident encode: d_ptr = device address of n_frames payloads back to back."""

@@ -126,6 +126,28 @@ def test_config3_frame_4k_16bit_roundtrip():
         enc.close()
 
 
+def test_two_host_batches_in_flight():
+    # b200_ffv1_submit_host: batch i+1 is coded while the packets of batch i are fetched; fetches come back oldest first
+    w, h, layout, slices = 256, 144, S.DPX_RGB_10_FA_BE, 4
+    enc = ffv1.FFV1Encoder(w, h, layout, slices=slices, max_frames=3)
+    try:
+        nh, nv = enc.grid
+        batches = [[S.synth_payload(w, h, layout, 500 + 10 * b + k, "grain" if (b + k) % 2 else "flat") for k in range(3 - (b == 2))] for b in range(4)]
+        want = [[util.oracle_encode(f, w, h, layout, nh, nv) for f in bt] for bt in batches]
+        enc.submit(batches[0])
+        enc.submit(batches[1])
+        assert [p.tobytes() for p in enc.fetch_packets(len(batches[0]))] == want[0]
+        enc.submit(batches[2])
+        assert [p.tobytes() for p in enc.fetch_packets(len(batches[1]))] == want[1]
+        enc.submit(batches[3])
+        assert [p.tobytes() for p in enc.fetch_packets(len(batches[2]))] == want[2]
+        assert [p.tobytes() for p in enc.fetch_packets(len(batches[3]))] == want[3]
+        # and the synchronous call still works afterwards
+        assert enc.encode(batches[1]) == want[1]
+    finally:
+        enc.close()
+
+
 def test_device_resident_entry_point():
     import torch
     w, h, layout, slices = 320, 240, S.DPX_RGB_16_BE, 4
