@@ -455,8 +455,8 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                         // black frames), the k-th of them sees state one_state^k(st) of slot 0 and nothing else moves: all of
                         // them at once, through the tables of one_state^(2^i)
                         bool have2 = have;
-                        {
-                            const bool z = have && v == 0;
+                        const bool z = have && v == 0;
+                        if (__any_sync(0xffffffffu, z)) {
                             const uint32_t mz = __match_any_sync(0xffffffffu, z ? cx : 0x40000u + (uint32_t)lane);
                             const bool pure = z && mz == mm;
                             if (__any_sync(0xffffffffu, pure)) {
