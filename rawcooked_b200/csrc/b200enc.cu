@@ -38,7 +38,9 @@ struct b200_ffv1_enc {
     b200_ffv1_cfg cfg;
     b200::Ffv1Stream st;
     b200::EncArgs args;             // band buffers of parity 0
-    static constexpr int kPar = 2;  // band-buffer sets in rotation (3 measured slower on B200: the extra model launches starve k_range of SMs)
+    static constexpr int kPar = 3;  // most band-buffer sets
+    int kpar = 2;                   // band-buffer sets in rotation (B200_KPAR=3 with B200_MODEL_RESERVE=36 measured +15 % at
+                                    // B = 128, but the optimum moves with B and with where the CTAs land: DESIGN.md §4)
     b200::EncArgs argsN[kPar];      // [0] unused (= args); [p] same as args with the band buffers of set p
     cudaStream_t sm = nullptr, sr = nullptr, se = nullptr;   // model / range / emit streams
     cudaStream_t sc = nullptr;                               // host-to-device copies of the host entry point
@@ -217,7 +219,8 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(A.ckptY, (size_t)B * ns * (A.capY >> 6) * 8);
     ALLOC(A.ckptC, (size_t)B * ns * (A.capC >> 6) * 8);
     ALLOC(A.used, (size_t)B * ns * 2 * 4);
-    for (int pz = 1; pz < b200_ffv1_enc::kPar; pz++) {
+    if (const char* e = getenv("B200_KPAR")) E->kpar = atoi(e) == 3 ? 3 : 2;
+    for (int pz = 1; pz < E->kpar; pz++) {
         b200::EncArgs& P = E->argsN[pz];
         ALLOC(P.qY, (size_t)B * ns * A.capY);
         ALLOC(P.qC, (size_t)B * ns * A.capC);
@@ -236,6 +239,14 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     ALLOC(A.frame_len, (size_t)B * 8);
     ALLOC(A.arena, A.arena_cap);
     ALLOC(A.flags, 256);
+    ALLOC(A.work_ctr, (size_t)A.nbands * 4);
+    {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
+        int reserve = 0;
+        if (const char* e = getenv("B200_MODEL_RESERVE")) reserve = atoi(e);
+        A.model_ctas = nsm - reserve > 1 ? nsm - reserve : 1;
+    }
 #undef ALLOC
     cudaMemcpy(d_geom, S.slices.data(), sizeof(b200::SliceGeom) * ns, cudaMemcpyHostToDevice);
     cudaMemcpy(d_qtab, S.qtab, sizeof S.qtab, cudaMemcpyHostToDevice);
@@ -245,7 +256,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     cudaMemcpy(d_hc, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d_crc, b200::crc32_mpeg_table(), 1024, cudaMemcpyHostToDevice);
     A.geom = d_geom; A.qtab = d_qtab; A.t1q = d_trans; A.tpow = d_tpow; A.hdr_bins = d_hb; A.hdr_cnt = d_hc; A.crc_table = d_crc;
-    for (int pz = 1; pz < b200_ffv1_enc::kPar; pz++) {
+    for (int pz = 1; pz < E->kpar; pz++) {
         const b200::EncArgs P = E->argsN[pz];
         E->argsN[pz] = A;
         b200::EncArgs& Q = E->argsN[pz];
@@ -342,13 +353,15 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
     constexpr int kPar = b200_ffv1_enc::kPar;
     b200::EncArgs A[kPar];
     A[0] = E->args;
-    for (int pz = 1; pz < kPar; pz++) A[pz] = E->argsN[pz];
+    for (int pz = 1; pz < E->kpar; pz++) A[pz] = E->argsN[pz];
+    for (int pz = E->kpar; pz < kPar; pz++) A[pz] = E->args;
     for (int pz = 0; pz < kPar; pz++) {
         A[pz].in = static_cast<const uint8_t*>(d_frames);
         A[pz].arena = R.arena; A[pz].slice_size = R.slice_size; A[pz].slice_off = R.slice_off; A[pz].frame_off = R.frame_off;
         A[pz].frame_len = R.frame_len; A[pz].flags = R.flags;
     }
     CU(cudaMemsetAsync(A[0].flags, 0, 256, s));
+    CU(cudaMemsetAsync(A[0].work_ctr, 0, (size_t)A[0].nbands * 4, s));
     CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)n_frames * A[0].nslices * A[0].slice_cap, s));   // k_emit accumulates into it
     // Three kernels per band on three streams: model(b) -> range(b) -> emit(b); model(b) reuses the band buffers of
     // parity b&1 once emit(b-2) has drained them. `s` (the caller's stream) forks into and joins from the three.
@@ -383,7 +396,7 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
         if (!serial) { CU(cudaEventRecord(E->ev_start, s)); CU(cudaStreamWaitEvent(E->sc, E->ev_start, 0)); }
     }
     for (int band = 0; band < nb; band++) {
-        const int p = band % kPar;
+        const int p = band % E->kpar;
         if (host_frames) {
             cudaStream_t sc = serial ? s : E->sc;
             const size_t rb = E->st.row_bytes;
@@ -398,7 +411,7 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
                 }
             if (!serial) { CU(cudaEventRecord(E->ev_h2d[band], sc)); CU(cudaStreamWaitEvent(sm, E->ev_h2d[band], 0)); }
         }
-        if (!serial && band >= kPar) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
+        if (!serial && band >= E->kpar) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 0], s));
         if (tr) CU(cudaEventRecord(E->trace[band * 6 + 0], sm));
         CU(b200::launch_model(A[p], band, n_frames, sm));

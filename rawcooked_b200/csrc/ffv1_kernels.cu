@@ -10,6 +10,8 @@
 //   pixel layouts + RCT     Source/Lib/Transform/Transform.cpp:29-37, :70-420
 #include "ffv1_kernels.cuh"
 
+#include <cstdlib>
+
 #include "../../include/b200enc.h"
 
 namespace b200 {
@@ -193,8 +195,7 @@ __device__ __forceinline__ void slot_step(const uint32_t (&S0)[8], uint32_t (&S)
 }
 
 template <bool kCompact, bool kRep>
-__device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t* smem_raw) {
-    const int slice = blockIdx.x >> 1, ps = blockIdx.x & 1, frame = blockIdx.y;
+__device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t* smem_raw, int slice, int ps, int frame) {
     const SliceGeom g = A.geom[slice];
     const int r0 = band * A.band_rows;
     if (r0 >= g.h) return;
@@ -655,17 +656,34 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     }
 }
 
-__global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_body<false, true>(A, band, smem_raw);
+// Persistent grid: every CTA pulls (frame, slice, plane-set) items from a counter until none is left, the Cb/Cr items (twice
+// the work) first. The grid is the number of SMs minus the ones left to k_range and k_emit, which must never wait behind
+// queued model CTAs (launch_model).
+template <bool kCompact, bool kRep>
+__device__ __forceinline__ void k_model_loop(const EncArgs& A, int band, int nframes, uint8_t* smem_raw) {
+    __shared__ int s_item;
+    const int nfs = nframes * A.nslices, nitems = nfs * 2;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(A.work_ctr + band, 1u);
+        __syncthreads();
+        const int wk = s_item;
+        if (wk >= nitems) break;
+        const int ps = wk < nfs ? 1 : 0, fsl = wk < nfs ? wk : wk - nfs;
+        k_model_body<kCompact, kRep>(A, band, smem_raw, fsl % A.nslices, ps, fsl / A.nslices);
+    }
 }
-__global__ void __launch_bounds__(kModelThreads, 1) k_model_lean(const __grid_constant__ EncArgs A, int band) {
+__global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band, int nframes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_body<false, false>(A, band, smem_raw);
+    k_model_loop<false, true>(A, band, nframes, smem_raw);
 }
-__global__ void __launch_bounds__(kModelThreads, 1) k_model_compact(const __grid_constant__ EncArgs A, int band) {
+__global__ void __launch_bounds__(kModelThreads, 1) k_model_lean(const __grid_constant__ EncArgs A, int band, int nframes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_body<true, false>(A, band, smem_raw);
+    k_model_loop<false, false>(A, band, nframes, smem_raw);
+}
+__global__ void __launch_bounds__(kModelThreads, 1) k_model_compact(const __grid_constant__ EncArgs A, int band, int nframes) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    k_model_loop<true, false>(A, band, nframes, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1016,7 +1034,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ E
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-typedef void (*model_fn)(const EncArgs, int);
+typedef void (*model_fn)(const EncArgs, int, int);
 static model_fn pick_model(const EncArgs& a) { return a.sstride != 32 ? k_model_compact : (a.first_n > 0 ? k_model : k_model_lean); }
 
 cudaError_t configure_kernels(const EncArgs& a) {
@@ -1032,9 +1050,10 @@ cudaError_t configure_kernels(const EncArgs& a) {
 }
 
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s) {
-    dim3 grid(a.nslices * 2, nframes);
     const size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.first_n, a.stage_cap);
-    pick_model(a)<<<grid, kModelThreads, smem, s>>>(a, band);
+    int grid = a.model_ctas;
+    if (grid > nframes * a.nslices * 2) grid = nframes * a.nslices * 2;
+    pick_model(a)<<<grid, kModelThreads, smem, s>>>(a, band, nframes);
     return cudaGetLastError();
 }
 
@@ -1043,7 +1062,13 @@ cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s
     // k_range is one latency-critical warp per CTA: beside k_model's warps (or more than two of its own kind per scheduler) it
     // slows down by the scheduler's round-robin factor. The (unused) dynamic shared memory keeps it at 8 CTAs per SM and off
     // the SMs k_model occupies; its high-priority stream hands it the first SMs k_model's CTAs leave.
-    k_range<<<(n + 31) / 32, 32, 28 * 1024, s>>>(a, band, nframes);
+    static int range_smem = 0;
+    if (!range_smem) {
+        range_smem = 28 * 1024;
+        if (const char* e = getenv("B200_RANGE_SMEM_KB")) range_smem = atoi(e) * 1024;
+        if (range_smem > 48 * 1024) cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize, range_smem);
+    }
+    k_range<<<(n + 31) / 32, 32, range_smem, s>>>(a, band, nframes);
     return cudaGetLastError();
 }
 

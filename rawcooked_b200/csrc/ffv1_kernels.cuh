@@ -77,6 +77,8 @@ struct EncArgs {
     uint64_t* frame_len;          // [frames]
     uint8_t* arena;
     size_t arena_cap;
+    uint32_t* work_ctr;           // [nbands] next work item of k_model's persistent grid (zeroed per encode call)
+    int32_t model_ctas;           // CTAs of k_model's grid (SMs minus the ones left to k_range / k_emit)
     uint32_t* flags;              // [0] overflow flag, [2..3] total bins, [16..] phase cycles (-DB200_PHASE_TIMING)
 };
 
