@@ -6,9 +6,9 @@
 //                         probability of the coded value; q = 255 is a no-op used for padding) and one bit (the coded value)
 //                         in a separate bit-plane.
 //   k_range  (K4a)        one lane per (frame, slice): the strictly serial recurrence of `range` and the byte count;
-//                         leaves a checkpoint every 128 records.
-//   k_emit   (K4b)        one thread per 128-record block: replays the block from its checkpoint and adds its bytes
-//                         into the slice stream.
+//                         leaves a checkpoint every 64 records.
+//   k_emit   (K4b)        one thread per 64 records: replays them from the checkpoint and adds their bytes into the
+//                         slice stream.
 //   k_scan / k_pack       slice sizes -> packet layout; compaction of the per-slice byte streams into packets, CRC, footer.
 //
 // Frames are processed in horizontal bands of `band_rows` rows so that the bin records (the only large intermediate)
@@ -29,7 +29,7 @@ namespace b200 {
 constexpr int kModelThreads = B200_MODEL_THREADS;   // one CTA per SM when the large context model (162 KB) is in smem
 constexpr int kModelWarps = kModelThreads / 32;
 constexpr int kMaxHeaderBins = 96;
-constexpr int kBlockRecs = 128;                     // records per coder block (checkpoint granularity)
+constexpr int kBlockRecs = 128;                     // every plane-row segment is padded to a multiple of this many records
 constexpr int kMaxSeg = 4;                          // column segments a plane-row may be coded in (stage capacity)
 constexpr int kModelSmemReserve = 4 * 1024;         // left free per SM so that k_range CTAs (no shared memory) co-reside
 
@@ -48,7 +48,7 @@ struct EncArgs {
     int32_t band_rows, nbands, wmax, hmax;
     int32_t stage_cap;            // records of one plane-row segment k_model stages in shared memory
     int32_t nseg;                 // column segments per plane-row reserved in rowcnt (1..kMaxSeg)
-    int32_t first_n;              // entries of the first-occurrence table (>= nctx: direct, else a power of two: hashed)
+    int32_t first_n;              // > 0: one_state table replicated per bank in k_model's shared memory, < 0: plain table
     const SliceGeom* geom;        // [nslices]
     const int16_t* qtab;          // [5][256]
     const uint8_t* t1q;           // [256] t1q[q] = one_state[q + 1]
@@ -65,9 +65,9 @@ struct EncArgs {
     uint8_t* bC;                  // [frames][nslices][capC/8]
     size_t capY, capC;            // records per (frame, slice) region, multiples of kBlockRecs
     uint32_t* rowcnt;             // [frames][nslices][band_rows][3][nseg]  records of each segment of the Y, Cb, Cr row
-    uint2* ckptY;                 // [frames][nslices][capY/128]  (range, bytes so far) at the head of every block
-    uint2* ckptC;                 // [frames][nslices][capC/128]
-    uint32_t* used;               // [frames][nslices][2]  blocks in use in the Y / C stream of this band
+    uint2* ckptY;                 // [frames][nslices][capY/64]  (range, bytes so far) every 64 records
+    uint2* ckptC;                 // [frames][nslices][capC/64]
+    uint32_t* used;               // [frames][nslices][2]  64-record pieces in use in the Y / C stream of this band
     CoderState* cstate;           // [frames][nslices]
     uint8_t* scratch;             // [frames][nslices][slice_cap]
     size_t slice_cap;
