@@ -73,3 +73,26 @@ def test_rawcooked_dpx_plus_wav(tmp_path):
     code, out = run_rawcooked(["--check", "-y", "-b", B200ENC, name], cwd=str(tmp_path))
     assert code == 0, out
     assert OK in out, out
+
+
+def test_rawcooked_tiff_plus_6ch_96k_wav(tmp_path):
+    # BASELINE config 4 in small: 16-bit RGB TIFF sequence + 24-bit / 96 kHz / 6-channel WAV (FFV1 + FLAC together)
+    name = "tiffpkg"
+    seq = tmp_path / name
+    os.makedirs(seq)
+    w, h, layout = 192, 108, S.TIFF_RGB_16_LE
+    for i in range(5):
+        payload = S.synth_payload(w, h, layout, 300 + i, "grain")
+        open(seq / ("t_%06d.tif" % i), "wb").write(S.tiff_file(w, h, layout, payload))
+    pcm = S.wav_pcm(6, 96000, 24, 20000, 78)
+    open(seq / "audio.wav", "wb").write(S.wav_file(pcm, 96000, 24))
+    code, out = run_rawcooked(["--check", "-y", "-b", B200ENC, name], cwd=str(tmp_path))
+    assert code == 0, out
+    assert OK in out, out
+    # flip one audio byte: the check against the source files must now fail
+    victim = seq / "audio.wav"
+    b = bytearray(victim.read_bytes())
+    b[len(b) // 2] ^= 0x01
+    victim.write_bytes(bytes(b))
+    code2, out2 = run_rawcooked(["--check", name + ".mkv", "-o", "./"], cwd=str(tmp_path))
+    assert OK not in out2 and ("not same" in out2 or code2 != 0), out2

@@ -126,6 +126,20 @@ def test_config3_frame_4k_16bit_roundtrip():
         enc.close()
 
 
+def test_config5_frame_8k_12bit():
+    # one frame of BASELINE config 5 (7680x4320 12-bit Filled-A BE, -slices 64 = 8x8): 960-px slices, column segments when a
+    # row's records outgrow the stage
+    w, h, layout = 7680, 4320, S.DPX_RGB_12_FA_BE
+    enc = ffv1.FFV1Encoder(w, h, layout, slices=64, max_frames=1)
+    try:
+        assert enc.grid == (8, 8)
+        f = S.synth_payload(w, h, layout, 5000)
+        p = enc.encode([f])[0]
+        assert p == util.oracle_encode(f, w, h, layout, 8, 8)
+    finally:
+        enc.close()
+
+
 def test_two_host_batches_in_flight():
     # b200_ffv1_submit_host: batch i+1 is coded while the packets of batch i are fetched; fetches come back oldest first
     w, h, layout, slices = 256, 144, S.DPX_RGB_10_FA_BE, 4
