@@ -4,10 +4,11 @@ import numpy as np, torch
 from rawcooked_b200 import ffv1, synth as S
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 kind = sys.argv[2] if len(sys.argv) > 2 else "grain"
-w, h, layout = 3840, 2160, S.DPX_RGB_16_BE
+w, h, layout = int(os.environ.get("PROBE_W", 3840)), int(os.environ.get("PROBE_H", 2160)), int(os.environ.get("PROBE_LAYOUT", S.DPX_RGB_16_BE))
+slices = int(os.environ.get("PROBE_SLICES", 24))
 uniq = [S.synth_payload(w, h, layout, 3000 + k, kind) for k in range(2)]
 d = torch.stack([torch.from_numpy(uniq[k % 2]) for k in range(B)]).cuda()
-enc = ffv1.FFV1Encoder(w, h, layout, slices=24, max_frames=B)
+enc = ffv1.FFV1Encoder(w, h, layout, slices=slices, max_frames=B)
 for it in range(3):
     torch.cuda.synchronize(); t = time.perf_counter()
     enc.encode_device(d.data_ptr(), B, 0)
