@@ -147,7 +147,11 @@ constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
 #ifndef B200_DENSE_MIN
 #define B200_DENSE_MIN 3      // measured on B200: 1 -> 219 ms, 3 -> 202, 5 -> 210, 7 -> 226, 10 -> 247, 16 -> 287 per 64 4K frames
 #endif
-constexpr int kDenseMin = B200_DENSE_MIN;           // rounds with fewer samples than this run one sample per step (one lane per slot)
+constexpr int kDenseMin = B200_DENSE_MIN;
+#ifndef B200_CHAIN_MIN
+#define B200_CHAIN_MIN 5
+#endif
+constexpr int kChainMin = B200_CHAIN_MIN;      // a context with at least this many samples in a batch is coded as a chain           // rounds with fewer samples than this run one sample per step (one lane per slot)
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
@@ -477,11 +481,61 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                 have2 = have && !pure;
                             }
                         }
-                        const int maxr = __reduce_max_sync(0xffffffffu, have2 ? rank : 0);
                         const bool nz = v != 0;
                         const uint32_t a = (uint32_t)abs(v);
                         const int e = nz ? 31 - __clz(a) : -1;
                         const bool neg = v < 0;
+                        // ---- chains: a context used by kChainMin or more samples of the batch (low-noise and flat content: a
+                        // handful of contexts take most of a row) is coded as one chain: lane s keeps the state of slot s in a
+                        // register from the first to the last sample; what a sample does to the 32 slots comes as two masks
+                        // (slot used / bin value) its own lane has prepared, so a step is a dozen instructions and the only
+                        // dependency from sample to sample is one table look-up. Symbols with exponent > 9 (two slots used more
+                        // than once) keep to the rounds below.
+                        {
+                            const int gsz = __popc(mm);
+                            const bool big = have2 && gsz >= kChainMin;
+                            const uint32_t bigm = __ballot_sync(0xffffffffu, big);
+                            const uint32_t wide = __ballot_sync(0xffffffffu, big && e > 9);
+                            if (bigm) {
+                                // a group is chained only if none of its members has e > 9
+                                const bool chain = big && (mm & wide) == 0;
+                                uint32_t um = 1u, bmk = nz ? 0u : 1u;
+                                if (nz && e <= 9) {
+                                    const uint32_t le = (1u << e) - 1u;
+                                    um = 1u | ((((1u << (e + 1)) - 1u)) << 1) | (1u << (11 + e)) | (le << 22);
+                                    bmk = (le << 1) | ((neg ? 1u : 0u) << (11 + e)) | ((a & le) << 22);
+                                }
+                                const uint32_t oe = o | ((uint32_t)(e < 0 ? 0 : e) << 24);
+                                // record index of my slot's bin inside a symbol of exponent e: kA + kE * e
+                                const int kA = lane == 0 ? 0 : isB ? lane : isD ? 2 : 23 - lane, kE = (lane == 0 || isB) ? 0 : 2;
+                                uint32_t leaders = __ballot_sync(0xffffffffu, chain && rank == 0);
+                                while (leaders) {
+                                    const int L = __ffs(leaders) - 1;
+                                    leaders &= leaders - 1;
+                                    uint32_t members = __shfl_sync(0xffffffffu, mm, L);
+                                    const uint32_t cj = __shfl_sync(0xffffffffu, cx, L);
+                                    const uint32_t sp = states_a + cj * (uint32_t)kRow + (uint32_t)lslot;
+                                    uint32_t st = lane_has_slot ? lds_u8_volatile(sp) : 128u;
+                                    while (members) {
+                                        const int j = __ffs(members) - 1;
+                                        members &= members - 1;
+                                        const uint32_t umj = __shfl_sync(0xffffffffu, um, j), bmj = __shfl_sync(0xffffffffu, bmk, j);
+                                        const uint32_t oej = __shfl_sync(0xffffffffu, oe, j);
+                                        const bool bit = (bmj >> lane) & 1u;
+                                        const int s1 = bit ? 1 : -1;
+                                        const uint32_t rec = (uint32_t)((int)st * s1 + 255);
+                                        if ((umj >> lane) & 1u) {
+                                            sts_u16(stage_a + ((oej & 0xFFFFFFu) + (uint32_t)(kA + kE * (int)(oej >> 24))) * 2u, rec);
+                                            st = (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
+                                        }
+                                    }
+                                    if (lane_has_slot) sts_u8(sp, st);
+                                }
+                                __syncwarp();
+                                have2 = have2 && !chain;
+                            }
+                        }
+                        const int maxr = __reduce_max_sync(0xffffffffu, have2 ? rank : 0);
                         for (int rr = 0; rr <= maxr; rr++) {
                             const bool act = have2 && rank == rr;
                             const uint32_t am = __ballot_sync(0xffffffffu, act);
