@@ -147,11 +147,11 @@ constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
 #ifndef B200_DENSE_MIN
 #define B200_DENSE_MIN 3      // measured on B200: 1 -> 219 ms, 3 -> 202, 5 -> 210, 7 -> 226, 10 -> 247, 16 -> 287 per 64 4K frames
 #endif
-constexpr int kDenseMin = B200_DENSE_MIN;
+constexpr int kDenseMin = B200_DENSE_MIN;        // rounds with fewer samples than this run one sample per step (one lane per slot)
 #ifndef B200_CHAIN_MIN
-#define B200_CHAIN_MIN 5
+#define B200_CHAIN_MIN 3       // measured on B200 (ms per 64 grainy 4K frames): 2 -> 192, 3 -> 193, 5 -> 199, 8 -> 205; low-noise content is indifferent
 #endif
-constexpr int kChainMin = B200_CHAIN_MIN;      // a context with at least this many samples in a batch is coded as a chain           // rounds with fewer samples than this run one sample per step (one lane per slot)
+constexpr int kChainMin = B200_CHAIN_MIN;      // a context with at least this many samples in a batch is coded as a chain
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
