@@ -164,7 +164,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
         delete E;
         return fail(B200_ERR_INVALID, "slice too wide for the shared-memory context model: use more slices");
     }
-    A.first_n = tries[best];
+    A.t1_rep = tries[best];
     A.stage_cap = (int32_t)best_cap;
     A.nseg = best_nseg;
     if (A.band_rows * 3 * A.nseg > 4096) { delete E; return fail(B200_ERR_INVALID, "band too large"); }

@@ -104,9 +104,9 @@ struct ModelSmem {
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-// bytes of everything except the record staging area. first_n > 0: t1 replicated per bank.
-size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int first_n) {
-    const bool rep = first_n > 0;
+// bytes of everything except the record staging area. t1_rep > 0: one_state table replicated per bank, else a plain table.
+size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int t1_rep) {
+    const bool rep = t1_rep > 0;
     size_t n = align16((size_t)nctx * sstride);
     n += align16((size_t)3 * planes * wmax * 4);
     n += 5 * 256 * 2;
@@ -120,12 +120,12 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int first_n
     n += 5 * 256;                            // tpow
     return n;
 }
-size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int first_n, int stage_cap) {
-    return model_smem_fixed(nctx, sstride, wmax, planes, first_n) + align16((size_t)stage_cap * 2);
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int t1_rep, int stage_cap) {
+    return model_smem_fixed(nctx, sstride, wmax, planes, t1_rep) + align16((size_t)stage_cap * 2);
 }
 
-__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes, int first_n) {
-    const bool rep = first_n > 0;
+__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes, int t1_rep) {
+    const bool rep = t1_rep > 0;
     ModelSmem m;
     m.states = base; base += align16((size_t)nctx * sstride);
     m.ring = reinterpret_cast<int32_t*>(base); base += align16((size_t)3 * planes * wmax * 4);
@@ -210,7 +210,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     constexpr int NW = kModelThreads / 32;
     constexpr int kRow = kCompact ? 28 : 32;                   // state bytes per context
     constexpr int kWords = kCompact ? 7 : 8;
-    const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, planes, A.first_n);
+    const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, planes, A.t1_rep);
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
     T1<kRep> t1;
     t1.base = smem_addr(S.t1b) + (kRep ? lane * 4 : 0);
@@ -1089,10 +1089,10 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ E
 
 // ------------------------------------------------------------------------------------------------------------------
 typedef void (*model_fn)(const EncArgs, int, int);
-static model_fn pick_model(const EncArgs& a) { return a.sstride != 32 ? k_model_compact : (a.first_n > 0 ? k_model : k_model_lean); }
+static model_fn pick_model(const EncArgs& a) { return a.sstride != 32 ? k_model_compact : (a.t1_rep > 0 ? k_model : k_model_lean); }
 
 cudaError_t configure_kernels(const EncArgs& a) {
-    const size_t need = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.first_n, a.stage_cap);
+    const size_t need = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.t1_rep, a.stage_cap);
     // every kernel asks for the same L1 / shared-memory split as k_model: an SM cannot hold CTAs of two kernels that want
     // different splits, and k_range / k_emit / k_pack must run beside k_model's CTAs, not after them
     cudaFuncSetAttribute(k_range, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1104,7 +1104,7 @@ cudaError_t configure_kernels(const EncArgs& a) {
 }
 
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s) {
-    const size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.first_n, a.stage_cap);
+    const size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.t1_rep, a.stage_cap);
     int grid = a.model_ctas;
     if (grid > nframes * a.nslices * 2) grid = nframes * a.nslices * 2;
     pick_model(a)<<<grid, kModelThreads, smem, s>>>(a, band, nframes);
