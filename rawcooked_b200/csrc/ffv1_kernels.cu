@@ -100,7 +100,7 @@ constexpr uint32_t kNopRec = 0x00FFu;
 // barrier inside S2.
 struct ModelSmem {
     uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b;
-    int32_t* val; uint16_t* ctx; uint16_t* off; uint32_t* ctot; uint32_t* cmask; uint32_t* misc; uint8_t* tpow; uint16_t* stage;
+    int32_t* val; uint16_t* ctx; uint16_t* off; uint32_t* ctot; uint32_t* cmask; uint32_t* misc; uint8_t* tpow; uint8_t* trans; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -118,6 +118,7 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int t1_rep)
     n += (size_t)nch * kModelWarps * 4;      // cmask
     n += kModelWarps * 64;                   // misc: per-lane landing place of the records of idle lanes
     n += 5 * 256;                            // tpow
+    n += 512;                                // trans
     return n;
 }
 size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int t1_rep, int stage_cap) {
@@ -139,6 +140,7 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     m.cmask = reinterpret_cast<uint32_t*>(base); base += (size_t)nch * kModelWarps * 4;
     m.misc = reinterpret_cast<uint32_t*>(base); base += kModelWarps * 64;
     m.tpow = base; base += 5 * 256;
+    m.trans = base; base += 512;
     m.stage = reinterpret_cast<uint16_t*>(base);
     return m;
 }
@@ -215,7 +217,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     T1<kRep> t1;
     t1.base = smem_addr(S.t1b) + (kRep ? lane * 4 : 0);
     const uint32_t dummy = smem_addr(S.misc) + warp * 64 + lane * 2;   // where the lanes that have no bin in a step put their record
-    const uint32_t stage_a = smem_addr(S.stage), states_a = smem_addr(S.states), tpow_a = smem_addr(S.tpow);
+    const uint32_t stage_a = smem_addr(S.stage), states_a = smem_addr(S.states), tpow_a = smem_addr(S.tpow), trans_a = smem_addr(S.trans);
     const uint32_t lt = (1u << lane) - 1u;
 
     const size_t fs = (size_t)frame * A.nslices + slice;
@@ -239,6 +241,11 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
         }
         for (int i = tid; i < ((wmax + 31) / 32) * NW; i += kModelThreads) S.cmask[i] = 0;
         for (int i = tid; i < 5 * 256; i += kModelThreads) S.tpow[i] = A.tpow[i];
+        // next state by (bit, state): the chains' only dependency from sample to sample is one look-up in this table
+        for (int i = tid; i < 512; i += kModelThreads) {
+            const int st = i & 255;
+            S.trans[i] = st == 0 ? (uint8_t)0 : (i >> 8) ? A.t1q[st - 1] : (uint8_t)(256 - A.t1q[255 - st]);
+        }
     }
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
@@ -505,9 +512,12 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                     um = 1u | ((((1u << (e + 1)) - 1u)) << 1) | (1u << (11 + e)) | (le << 22);
                                     bmk = (le << 1) | ((neg ? 1u : 0u) << (11 + e)) | ((a & le) << 22);
                                 }
-                                const uint32_t oe = o | ((uint32_t)(e < 0 ? 0 : e) << 24);
-                                // record index of my slot's bin inside a symbol of exponent e: kA + kE * e
-                                const int kA = lane == 0 ? 0 : isB ? lane : isD ? 2 : 23 - lane, kE = (lane == 0 || isB) ? 0 : 2;
+                                // record index of my slot's bin inside a symbol of exponent e: kA + kE * e with kE = 0 (zero flag,
+                                // exponent) or 2 (sign, mantissa): the sample hands over both byte offsets, 2o and 2o + 4e, in one word
+                                const int kA = lane == 0 ? 0 : isB ? lane : isD ? 2 : 23 - lane;
+                                const uint32_t ee = (uint32_t)(e < 0 ? 0 : e);
+                                const uint32_t ow = (2u * o) | ((2u * o + 4u * ee) << 16);
+                                const uint32_t abase = stage_a + 2u * (uint32_t)kA, hs = (lane == 0 || isB) ? 0u : 16u, lbit = 1u << lane;
                                 uint32_t leaders = __ballot_sync(0xffffffffu, chain && rank == 0);
                                 while (leaders) {
                                     const int L = __ffs(leaders) - 1;
@@ -520,13 +530,13 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                         const int j = __ffs(members) - 1;
                                         members &= members - 1;
                                         const uint32_t umj = __shfl_sync(0xffffffffu, um, j), bmj = __shfl_sync(0xffffffffu, bmk, j);
-                                        const uint32_t oej = __shfl_sync(0xffffffffu, oe, j);
-                                        const bool bit = (bmj >> lane) & 1u;
+                                        const uint32_t owj = __shfl_sync(0xffffffffu, ow, j);
+                                        const bool bit = (bmj & lbit) != 0;
                                         const int s1 = bit ? 1 : -1;
                                         const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                        if ((umj >> lane) & 1u) {
-                                            sts_u16(stage_a + ((oej & 0xFFFFFFu) + (uint32_t)(kA + kE * (int)(oej >> 24))) * 2u, rec);
-                                            st = (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
+                                        if (umj & lbit) {
+                                            sts_u16(abase + ((owj >> hs) & 0xFFFFu), rec);
+                                            st = lds_u8(trans_a + st + (bit ? 256u : 0u));
                                         }
                                     }
                                     if (lane_has_slot) sts_u8(sp, st);
