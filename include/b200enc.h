@@ -88,6 +88,11 @@ void b200_ffv1_close(b200_ffv1_enc* enc);
  * check at FFV1_Frame.cpp:114-117). Returns its size; copies min(size, cap) bytes. */
 size_t b200_ffv1_config_record(const b200_ffv1_enc* enc, uint8_t* out, size_t cap);
 
+/* The same record computed on the host alone, without opening an encoder (no device needed): what a muxer that writes the
+ * track header before the first frame is encoded would call. Returns the size (0 and b200_last_error() on a bad configuration);
+ * copies min(size, cap) bytes. */
+size_t b200_ffv1_config_record_for(const b200_ffv1_cfg* cfg, uint8_t* out, size_t cap);
+
 /* Upper bound of one packet's size, for sizing `out` below. */
 size_t b200_ffv1_max_packet_bytes(const b200_ffv1_enc* enc);
 

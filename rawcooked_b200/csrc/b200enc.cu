@@ -327,6 +327,18 @@ size_t b200_ffv1_config_record(const b200_ffv1_enc* E, uint8_t* out, size_t cap)
     return n;
 }
 
+size_t b200_ffv1_config_record_for(const b200_ffv1_cfg* cfg, uint8_t* out, size_t cap) {
+    if (!cfg) { fail(B200_ERR_INVALID, "null argument"); return 0; }
+    if (cfg->coder != 1) { fail(B200_ERR_INVALID, "only -coder 1 (range coder) is implemented"); return 0; }
+    b200::Ffv1Stream st;
+    const char* err = "";
+    const int r = b200::build_stream(cfg->width, cfg->height, cfg->layout, cfg->slices, cfg->context, cfg->slicecrc, &st, &err);
+    if (r) { fail(r, err); return 0; }
+    const size_t n = st.config_record.size();
+    if (out && cap) std::memcpy(out, st.config_record.data(), n < cap ? n : cap);
+    return n;
+}
+
 size_t b200_ffv1_max_packet_bytes(const b200_ffv1_enc* E) { return E ? E->max_packet : 0; }
 
 int b200_ffv1_set_timing(b200_ffv1_enc* E, int32_t enabled) {

@@ -42,6 +42,8 @@ def load_library():
     L.b200_ffv1_close.restype = None
     L.b200_ffv1_config_record.restype = C.c_size_t
     L.b200_ffv1_config_record.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.b200_ffv1_config_record_for.restype = C.c_size_t
+    L.b200_ffv1_config_record_for.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_size_t]
     L.b200_ffv1_max_packet_bytes.restype = C.c_size_t
     L.b200_ffv1_max_packet_bytes.argtypes = [C.c_void_p]
     L.b200_ffv1_encode_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t,
@@ -67,6 +69,18 @@ def slice_grid(width, height, slices):
     nh, nv = C.c_int32(0), C.c_int32(0)
     _check(L.b200_ffv1_slice_grid(width, height, slices, C.byref(nh), C.byref(nv)))
     return nh.value, nv.value
+
+
+def config_record(width, height, layout, slices=0, context=1, slicecrc=1):
+    """FFV1 ConfigurationRecord (Matroska CodecPrivate) for this option set, computed on the host: no device needed."""
+    L = load_library()
+    cfg = _Cfg(width, height, layout, slices, context, 1, slicecrc, 1, 0)
+    n = L.b200_ffv1_config_record_for(C.byref(cfg), None, 0)
+    if n == 0:
+        raise B200Error(-1, L.b200_last_error().decode())
+    buf = C.create_string_buffer(n)
+    L.b200_ffv1_config_record_for(C.byref(cfg), buf, n)
+    return buf.raw[:n]
 
 
 def frame_bytes(width, height, layout):
