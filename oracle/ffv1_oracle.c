@@ -64,8 +64,8 @@ size_t ffv1o_row_bytes(uint32_t w, int layout)
     case L_TIFF_RGB_8: return (size_t)w * 3;
     case L_DPX_RGB_10_FA_LE: case L_DPX_RGB_10_FA_BE: return (size_t)w * 4;
     case L_DPX_RGB_12_PACKED_BE: return (((size_t)w * 36 + 31) / 32) * 4;
-    case L_DPX_RGB_12_FA_LE: case L_DPX_RGB_12_FA_BE:
-    case L_DPX_RGB_16_LE: case L_DPX_RGB_16_BE: case L_TIFF_RGB_16_LE: case L_TIFF_RGB_16_BE: return (size_t)w * 6;
+    case L_DPX_RGB_16_LE: case L_DPX_RGB_16_BE: return ((size_t)w * 6 + 3) & ~(size_t)3;   /* not a Filled packing: DPX.cpp:478-482 */
+    case L_DPX_RGB_12_FA_LE: case L_DPX_RGB_12_FA_BE: case L_TIFF_RGB_16_LE: case L_TIFF_RGB_16_BE: return (size_t)w * 6;
     }
     return 0;
 }

@@ -26,8 +26,10 @@ size_t layout_row_bytes(uint32_t w, int layout) {
         case B200_TIFF_RGB_8: return (size_t)w * 3;
         case B200_DPX_RGB_10_FILLED_A_LE: case B200_DPX_RGB_10_FILLED_A_BE: return (size_t)w * 4;
         case B200_DPX_RGB_12_PACKED_BE: return (((size_t)w * 36 + 31) / 32) * 4;
+        // 16-bit DPX is not a "Filled" packing: its rows take the 32-bit line padding of DPX.cpp:478-482 (odd widths: + 2 bytes),
+        // 12-bit Filled-A rows are whole 6-byte blocks (DPX.cpp:463-475), TIFF strips are tight
+        case B200_DPX_RGB_16_LE: case B200_DPX_RGB_16_BE: return ((size_t)w * 6 + 3) & ~(size_t)3;
         case B200_DPX_RGB_12_FILLED_A_LE: case B200_DPX_RGB_12_FILLED_A_BE:
-        case B200_DPX_RGB_16_LE: case B200_DPX_RGB_16_BE:
         case B200_TIFF_RGB_16_LE: case B200_TIFF_RGB_16_BE: return (size_t)w * 6;
     }
     return 0;

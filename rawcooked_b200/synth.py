@@ -50,6 +50,8 @@ def row_bytes(width, layout):
         return width * 4
     if layout == DPX_RGB_12_PACKED_BE:
         return ((width * 36 + 31) // 32) * 4
+    if layout in (DPX_RGB_16_LE, DPX_RGB_16_BE):
+        return (width * 6 + 3) & ~3          # DPX lines are padded to 32 bits unless the packing is "Filled" (DPX.cpp:478-482)
     return width * 6
 
 
@@ -72,7 +74,11 @@ def pack_payload(R, G, B, layout):
         sh = 4 if layout in (DPX_RGB_12_FA_LE, DPX_RGB_12_FA_BE) else 0
         le = layout in (DPX_RGB_12_FA_LE, DPX_RGB_16_LE, TIFF_RGB_16_LE)
         v = (np.stack([R, G, B], -1).astype(np.uint16) << sh)
-        return v.astype("<u2" if le else ">u2").view(np.uint8).reshape(-1)
+        rows = v.astype("<u2" if le else ">u2").view(np.uint8).reshape(h, 6 * w)
+        rb = row_bytes(w, layout)
+        if rb != 6 * w:
+            rows = np.pad(rows, ((0, 0), (0, rb - 6 * w)))
+        return np.ascontiguousarray(rows).reshape(-1)
     if layout == DPX_RGB_12_PACKED_BE:
         comps = np.stack([R, G, B], -1).reshape(h, 3 * w).astype(np.uint64)
         nwords = row_bytes(w, layout) // 4

@@ -74,11 +74,9 @@ def test_product_does_not_touch_oracle():
 def test_host_config_record_equals_ffmpeg_golden():
     # the ConfigurationRecord is host work (quantisation tables, state-transition table, slice grid, CRC): byte-identical to
     # the record libavcodec produced for every golden case, without a device
-    import os
-    import numpy as np
-    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ffv1_golden.npz"))
-    for i, m in enumerate(G["meta"]):
-        w, h, layout, slices, context, seed = (int(v) for v in m)
-        assert ffv1.config_record(w, h, layout, slices=slices, context=context) == G["record_%d" % i].tobytes(), (i, w, h, layout, slices, context)
+    import util
+    for i in range(util.golden_count()):
+        w, h, layout, slices, context, ec, _, rec, _ = util.golden_case(i)
+        assert ffv1.config_record(w, h, layout, slices=slices, context=context, slicecrc=ec) == rec, (i, w, h, layout, slices, context, ec)
     with pytest.raises(ffv1.B200Error):
         ffv1.config_record(1920, 1080, S.DPX_RGB_16_BE, slices=7)

@@ -115,6 +115,17 @@ def ref_decode(record, packet, width, height, layout, threads=1):
         raise RuntimeError("reference decoder: rc=%d %s" % (rc, err.value.decode()))
     from rawcooked_b200 import synth as S
     n = S.frame_bytes(width, height, layout)
+    # 8-bit and 16-bit DPX files pad every line to 32 bits (DPX.cpp:478-482, what the reference's parser sizes the file by and
+    # what ffmpeg's dpx decoder skips), but the decoder's plane holds whole 3- or 6-byte blocks back to back (RawFrame.h:118-131:
+    # a line is only aligned when it ends in an incomplete block). The padding is not pixel data: re-insert it as zeros so that
+    # the result compares with a zero-padded source payload.
+    valid = {S.DPX_RGB_8: 3 * width, S.DPX_RGB_16_LE: 6 * width, S.DPX_RGB_16_BE: 6 * width}.get(layout)
+    rb = S.row_bytes(width, layout)
+    if valid is not None and valid != rb:
+        assert osz.value - valid * height in range(0, 4), (osz.value, valid * height)
+        rows = np.zeros((height, rb), np.uint8)
+        rows[:, :valid] = out[:valid * height].reshape(height, valid)
+        return rows.tobytes()
     assert osz.value - n in range(0, 4), (osz.value, n)
     return out[:n].tobytes()
 
@@ -122,3 +133,30 @@ def ref_decode(record, packet, width, height, layout, threads=1):
 def ref_rawcooked():
     p = os.path.join(ORACLE_DIR, "_ref", "rawcooked")
     return p if os.path.exists(p) else None
+
+
+_golden = None
+
+
+def golden():
+    """tests/golden/ffv1_golden.npz: libavcodec's own records and packets (tests/golden/make_golden.py)."""
+    global _golden
+    if _golden is None:
+        _golden = np.load(os.path.join(ROOT, "tests", "golden", "ffv1_golden.npz"))
+    return _golden
+
+
+def golden_count():
+    return len(golden()["meta"])
+
+
+def golden_case(i):
+    """(w, h, layout, slices, context, slicecrc, payload, record, packet) of golden case i."""
+    from rawcooked_b200 import synth as S
+    G = golden()
+    w, h, layout, slices, context, seed, slicecrc = (int(v) for v in G["meta"][i])
+    kind = G["kind_%d" % i].tobytes().decode()
+    payload = G["payload_%d" % i]
+    if payload.size == 0:
+        payload = S.synth_payload(w, h, layout, seed, kind)
+    return w, h, layout, slices, context, slicecrc, payload, G["record_%d" % i].tobytes(), G["packet_%d" % i].tobytes()

@@ -15,5 +15,13 @@ for it in range(3):
     torch.cuda.synchronize(); dt = time.perf_counter() - t
     print("B=%d %s: %.1f ms  %.1f fps  %.1f MPix/s" % (B, kind, dt * 1e3, B / dt, B * w * h / dt / 1e6))
 arena, off, ln = enc.packets_device(B)
+if os.environ.get("PROBE_KERNELS"):
+    enc.set_timing(True)
+    enc.encode_device(d.data_ptr(), B, 0)
+    torch.cuda.synchronize()
+    enc.packets_device(B)
+    ts = enc.stats()
+    print("kernel ms per batch: model %.1f range %.1f emit %.1f pack %.1f" % (ts["model_us"] / 1e3, ts["range_us"] / 1e3, ts["emit_us"] / 1e3, ts["pack_us"] / 1e3))
+    enc.set_timing(False)
 st = enc.stats()
 print(st, "bins/sample", st["bins"] / st["samples"], "ratio", st["packet_bytes"] / (B * enc.frame_bytes))
