@@ -1,63 +1,104 @@
 #!/usr/bin/env python
-"""bench.py — FFV1 encode throughput of the B200 path on BASELINE.json's headline workload.
+"""bench.py — FFV1 (+FLAC) encode throughput of the B200 path on BASELINE.json's workloads.
 
-Workload (BASELINE.json configs[2], the one the metric is quoted on; it fits one GPU): UHD 4K (3840x2160) 16-bit RGB DPX
+Default workload = BASELINE config 3, the one the metric is quoted on (it fits one GPU): UHD 4K (3840x2160) 16-bit RGB DPX
 (big endian), `-slices 24` (6x4), `-context 1 -coder 1 -slicecrc 1 -level 3 -g 1` (RAWcooked's option set,
-/root/reference/Source/CLI/Global.cpp:938-989). One "step" = one batch of --frames synthetic frames per GPU through the
-whole hot path (k_model -> k_range -> k_emit -> k_scan/k_pack). Frames shard one batch per GPU (weak scaling); with N > 1
-the packets are gathered to rank 0 over NCCL inside the timed region (the path's only exchange step).
+/root/reference/Source/CLI/Global.cpp:938-989). `--config 2|4|5` runs the other BASELINE configurations with the same JSON
+shape (2: 2K 10-bit, 4 slices; 4: 4K 16-bit TIFF + 6-channel 96 kHz 24-bit FLAC together; 5: 8K 12-bit, 64 slices).
+One "step" = one batch of --frames synthetic frames per GPU through the whole hot path (k_model -> k_range -> k_emit ->
+k_scan/k_pack). Frames shard one batch per GPU (weak scaling); with N > 1 the packets are gathered to rank 0 over NCCL
+inside the timed region (the path's only exchange step), the gather of step i running behind the encode of
+step i+1.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--config C] [--impl b200|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line (rank 0). `--impl reference` times the reference's own CPU implementation of the path — FFmpeg's
-ffv1 encoder (libavcodec 62.11.100 from this image, the encoder RAWcooked shells out to), all host cores, on a bounded
-sample of the same workload.
+Prints ONE JSON line (rank 0). After the timed loops three packets of the LAST timed batch (first, middle, last frame) are
+checked: byte-identical to the oracle and decoded by the unmodified reference decoder back to the input payload; the line
+carries "check": "pass" and the process exits non-zero otherwise. `--impl reference` times the reference's own CPU
+implementation of the path — FFmpeg's ffv1 encoder (libavcodec 62.11.100 from this image, the encoder RAWcooked shells
+out to), all host cores — on a bounded sample of the same workload.
 """
 import argparse
+import ctypes as C
 import json
+import mmap
 import os
 import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 3840, 2160
-SLICES = 24
-METRIC = "MPix/s FFV1 encode, 4K 16-bit RGB DPX (3840x2160, 24 slices)"
+# BASELINE.json configs, numbered as in BASELINE.json's list counted from 1 (config 1 is the CPU plumbing case, no bench line)
+CONFIGS = {
+    2: dict(W=2048, H=1556, layout=2, slices=4, bits=10, noise=4, frames=128, fmt="gbrp10le", audio=False,
+            name="BASELINE config 2: 2K 2048x1556 10-bit RGB DPX (Filled-A, big endian), FFV1 v3, -slices 4 (2x2)"),
+    3: dict(W=3840, H=2160, layout=7, slices=24, bits=16, noise=256, frames=128, fmt="gbrp16le", audio=False,
+            name="BASELINE config 3: UHD 4K 3840x2160 16-bit RGB DPX (big endian), FFV1 v3, -slices 24 (6x4)"),
+    4: dict(W=3840, H=2160, layout=33, slices=24, bits=16, noise=256, frames=128, fmt="gbrp16le", audio=True,
+            name="BASELINE config 4: UHD 4K 3840x2160 16-bit RGB TIFF (little endian), FFV1 v3, -slices 24 (6x4) + "
+                 "24-bit 96 kHz 6-channel WAV -> FLAC, together"),
+    5: dict(W=7680, H=4320, layout=5, slices=64, bits=12, noise=16, frames=32, fmt="gbrp12le", audio=False,
+            name="BASELINE config 5: 8K 7680x4320 12-bit RGB DPX (Filled-A, big endian), FFV1 v3, -slices 64 (8x8)"),
+}
+AUDIO = dict(rate=96000, channels=6, bits=24, fps=24)
 
 
-def workload_config(frames, n_gpus):
+def metric_name(c):
+    if c["W"] == 3840 and not c["audio"]:
+        return "MPix/s FFV1 encode, 4K 16-bit RGB DPX (3840x2160, 24 slices)"
+    return "MPix/s FFV1 encode, %dx%d %d-bit RGB, %d slices%s" % (c["W"], c["H"], c["bits"], c["slices"], " + FLAC" if c["audio"] else "")
+
+
+def frame_bytes(c):
+    return c["W"] * c["H"] * (4 if c["bits"] == 10 else 6)
+
+
+def workload_config(c, frames, n_gpus):
     return {
-        "workload": "BASELINE configs[2]: UHD 4K 3840x2160 16-bit RGB DPX (big endian), FFV1 v3, -slices 24 (6x4), "
-                    "-context 1 -coder 1 -slicecrc 1 -level 3 -g 1; ramps + uniform noise +-256 (film-grain model), seeded",
+        "workload": c["name"] + ", -context 1 -coder 1 -slicecrc 1 -level 3 -g 1; ramps + uniform noise +-%d (film-grain model), seeded" % c["noise"],
         "frames_per_step_per_gpu": frames,
-        "frame_bytes": W * H * 6,
-        "sharding": "frame-parallel, one batch per GPU; packets gathered to rank 0 over NCCL" if n_gpus > 1 else "single GPU",
-        "l2": "inputs of one step (%.1f GB) are larger than L2 (126 MB); no flush needed" % (frames * W * H * 6 / 1e9),
+        "frame_bytes": frame_bytes(c),
+        "sharding": "frame-parallel, one batch per GPU; packets gathered to rank 0 over NCCL, behind the next step's encode" if n_gpus > 1 else "single GPU",
+        "l2": "inputs of one step (%.1f GB) are larger than L2 (126 MB); no flush needed" % (frames * frame_bytes(c) / 1e9),
     }
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def synth_frames_torch(n, seed, device):
-    """n DPX payloads (16-bit BE RGB) built on the GPU: per-channel ramps + uniform noise +-256. uint8 [n, W*H*6]."""
+def synth_frames_torch(c, n, seed, device):
+    """n payloads in the file layout of config c, built on the GPU: per-channel ramps + uniform noise. uint8 [n, frame_bytes]."""
     import torch
+    W, H, bits, layout, amp = c["W"], c["H"], c["bits"], c["layout"], c["noise"]
+    mx = (1 << bits) - 1
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     yy = torch.arange(H, device=device, dtype=torch.int64).view(H, 1)
     xx = torch.arange(W, device=device, dtype=torch.int64).view(1, W)
-    out = torch.empty((n, H, W, 3, 2), dtype=torch.uint8, device=device)
+    out = torch.empty((n, H * W * (4 if bits == 10 else 6)), dtype=torch.uint8, device=device)
     for i in range(n):
+        comp = []
         for k in range(3):
-            ramp = (xx * (k + 1) * 65535 // (3 * (W - 1)) + yy * (3 - k) * 65535 // (4 * (H - 1)) + 977 * i) % 65536
-            noise = torch.randint(-256, 257, (H, W), generator=g, device=device, dtype=torch.int64)
-            v = (ramp + noise).clamp_(0, 65535)
-            out[i, :, :, k, 0] = (v >> 8).to(torch.uint8)
-            out[i, :, :, k, 1] = (v & 255).to(torch.uint8)
-    return out.view(n, H * W * 6)
+            ramp = (xx * (k + 1) * mx // (3 * (W - 1)) + yy * (3 - k) * mx // (4 * (H - 1)) + 977 * i) % (mx + 1)
+            noise = torch.randint(-amp, amp + 1, (H, W), generator=g, device=device, dtype=torch.int64)
+            comp.append((ramp + noise).clamp_(0, mx))
+        if bits == 10:                                   # R<<22 | G<<12 | B<<2, big endian
+            v = (comp[0] << 22) | (comp[1] << 12) | (comp[2] << 2)
+            o = out[i].view(H, W, 4)
+            for b in range(4):
+                o[:, :, b] = ((v >> (8 * (3 - b))) & 255).to(torch.uint8)
+        else:
+            sh = 4 if bits == 12 else 0
+            le = layout == 33
+            o = out[i].view(H, W, 3, 2)
+            for k in range(3):
+                v = comp[k] << sh
+                o[:, :, k, 1 if le else 0] = (v >> 8).to(torch.uint8)
+                o[:, :, k, 0 if le else 1] = (v & 255).to(torch.uint8)
+    return out
 
 
 class ClockSampler:
@@ -109,91 +150,114 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(target_seconds, seed=4242, max_workers=None):
+class CpuReference:
     """FFmpeg's ffv1 encoder (libavcodec) on host cores, frame-parallel: one encoder context (threads=1) per worker so
-    that every core is busy (slice threading alone cannot use more cores than slices). Falls back to the C port."""
-    import numpy as np
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from rawcooked_b200 import synth as S
-    cores = os.cpu_count() or 1
-    try:
-        avail = len(os.sched_getaffinity(0))
-        cores = min(cores, avail)
-    except AttributeError:
-        pass
-    workers = max(1, min(cores, max_workers or 64))
-    R, G, B = S.rgb_content(W, H, 16, seed, "grain")
-    try:
-        import avcodec_ffv1 as A
-        A.version()
-        kind = "reference"
-    except Exception as e:          # noqa: BLE001
-        kind = "port"
-        err = str(e)
-    if kind == "reference":
-        encs = [A.FFV1Encoder(W, H, "gbrp16le", SLICES, threads=1) for _ in range(workers)]
-        for e in encs:
-            e.encode_planes([G, B, R])          # fills the frame buffer once + warm-up encode
-        t0 = time.perf_counter()
-        one = len(encs[0].encode_current())
-        t_one = time.perf_counter() - t0
-        per = max(1, int(target_seconds / max(t_one, 1e-3)))
-        done = [0] * workers
+    that every core is busy (slice threading alone cannot use more cores than slices). Content and encoder contexts are
+    built ONCE; run(n) then encodes n frames. Falls back to the C port of the oracle when libavcodec is missing."""
+
+    def __init__(self, c, seed=4242, max_workers=None):
+        import numpy as np  # noqa: F401
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        from rawcooked_b200 import synth as S
+        self.c = c
+        cores = os.cpu_count() or 1
+        try:
+            cores = min(cores, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            pass
+        self.workers = max(1, min(cores, max_workers or 64))
+        R, G, B = S.rgb_content(c["W"], c["H"], c["bits"], seed, "grain", noise=c["noise"])
+        try:
+            import avcodec_ffv1 as A
+            self.A = A
+            self.version = A.version()
+            self.kind = "reference"
+        except Exception as e:          # noqa: BLE001
+            self.kind = "port"
+            self.err = str(e)
+        if self.kind == "reference":
+            planes = [G, B, R]                       # gbrp* plane order
+            self.encs = [self.A.FFV1Encoder(c["W"], c["H"], c["fmt"], c["slices"], threads=1) for _ in range(self.workers)]
+            for e in self.encs:
+                self.packet = len(e.encode_planes(planes))      # fills the frame buffer once + warm-up encode
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import util
+            self.util = util
+            self.payload = S.pack_payload(R, G, B, c["layout"])
+            self.workers = 1
+
+    def run(self, n_frames):
+        """Encodes n_frames (spread over the workers); returns seconds."""
+        c = self.c
+        if self.kind == "port":
+            t0 = time.perf_counter()
+            for _ in range(n_frames):
+                nh, nv = {4: (2, 2), 24: (6, 4), 64: (8, 8)}[c["slices"]]
+                self.util.oracle_encode(self.payload, c["W"], c["H"], c["layout"], nh, nv)
+            return time.perf_counter() - t0
+        per = [n_frames // self.workers + (1 if i < n_frames % self.workers else 0) for i in range(self.workers)]
 
         def work(i):
-            for _ in range(per):
-                encs[i].encode_current()
-                done[i] += 1
-        ths = [threading.Thread(target=work, args=(i,)) for i in range(workers)]
+            for _ in range(per[i]):
+                self.encs[i].encode_current()
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(self.workers) if per[i]]
         t0 = time.perf_counter()
         for t in ths:
             t.start()
         for t in ths:
             t.join()
-        dt = time.perf_counter() - t0
-        n = sum(done)
-        for e in encs:
-            e.close()
-        sample = "%d frames of the workload (one seeded 4K16 frame re-encoded; intra-only, no state between frames), libavcodec %s ffv1 " \
-                 "coder=1 context=1 g=1 level=3 slicecrc=1 slices=24, %d encoder contexts x 1 thread, frame already in RAM, packet discarded; " \
-                 "%.1f s; packet %d bytes" % (n, A.version(), workers, dt, one)
-    else:
-        import ctypes as C
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import util
-        payload = S.pack_payload(R, G, B, S.DPX_RGB_16_BE)
-        t0 = time.perf_counter()
-        util.oracle_encode(payload, W, H, S.DPX_RGB_16_BE, 6, 4)
-        dt = time.perf_counter() - t0
-        n, workers = 1, 1
-        sample = "1 frame through oracle/ffv1_oracle.c (single thread); libavcodec unavailable: " + err
-    mpix = n * W * H / dt / 1e6
-    return {"value": mpix, "unit": "MPix/s", "cores": workers, "kind": kind, "sample": sample, "fps": n / dt, "seconds": dt}
+        return time.perf_counter() - t0
+
+    def describe(self, n_frames, seconds):
+        c = self.c
+        if self.kind == "port":
+            return "%d frame(s) through oracle/ffv1_oracle.c (single thread); libavcodec unavailable: %s" % (n_frames, self.err)
+        return ("%d frames of the workload (one seeded %dx%d %d-bit frame re-encoded; intra-only, no state between frames), libavcodec %s ffv1 "
+                "coder=1 context=1 g=1 level=3 slicecrc=1 slices=%d, %d encoder contexts x 1 thread, frame already in RAM, packet discarded; "
+                "%.1f s; packet %d bytes" % (n_frames, c["W"], c["H"], c["bits"], self.version, c["slices"], self.workers, seconds, self.packet))
+
+    def close(self):
+        if self.kind == "reference":
+            for e in self.encs:
+                e.close()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t0 = time.perf_counter()
-    per_step = max(4.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference_run(per_step)
+    c = CONFIGS[args.config]
+    t_wall = time.perf_counter()
+    ref = CpuReference(c)
+    # calibrate: one frame per worker
+    t_cal = ref.run(ref.workers)
+    fps_est = ref.workers / max(t_cal, 1e-3)
+    total_steps = args.steps + args.warmup
+    budget = 150.0                                       # seconds for all steps together
+    F = args.frames
+    sample = int(min(F, max(ref.workers, budget / total_steps * fps_est)))
+    sample = max(ref.workers, sample - sample % ref.workers)
+    secs = []
+    for i in range(total_steps):
+        dt = ref.run(sample)
         if i >= args.warmup:
-            vals.append(r)
-        base = r
-    v = sum(x["value"] for x in vals) / len(vals)
-    ms = 1e3 * sum(x["seconds"] for x in vals) / len(vals)
+            secs.append(dt)
+    dt = sum(secs) / len(secs)
+    v = sample * c["W"] * c["H"] / dt / 1e6
+    desc = ref.describe(sample, dt)
+    if sample != F:
+        desc += "; each step = a %d-frame sample of the %d-frame step, ms_per_step scaled by %d/%d" % (sample, F, F, sample)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args.frames, args.gpus),
-        "cpu_baseline": {"value": v, "unit": "MPix/s", "cores": base["cores"], "kind": base["kind"], "sample": base["sample"]},
+        "impl": "reference", "metric": metric_name(c), "value": v, "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt * F / sample, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(c, F, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "MPix/s", "cores": ref.workers, "kind": ref.kind, "sample": desc},
         "e2e": {"value": v, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "fps": v * 1e6 / (W * H), "wall_s": time.perf_counter() - t0,
+        "fps": v * 1e6 / (c["W"] * c["H"]), "sample_frames_per_step": sample,
     }
+    ref.close()
+    line["wall_s"] = time.perf_counter() - t_wall
     print(json.dumps(line), flush=True)
 
 
@@ -204,12 +268,32 @@ class _CudaBuf:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
 
 
+def check_packets(c, enc, payloads, packets):
+    """oracle equality + reference decode of a few packets (tests/util.py drives oracle/: the checker, not the product)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    nh, nv = enc.grid
+    detail = []
+    ok = True
+    for idx, (pay, pkt) in enumerate(zip(payloads, packets)):
+        want = util.oracle_encode(pay, c["W"], c["H"], c["layout"], nh, nv)
+        same = bytes(pkt) == want
+        dec = None
+        if util.ref_available():
+            dec = util.ref_decode(enc.config_record, bytes(pkt), c["W"], c["H"], c["layout"], threads=8) == pay.tobytes()
+        ok = ok and same and (dec is not False)
+        detail.append({"packet_bytes": len(pkt), "equals_oracle": same, "reference_decode_equals_input": dec})
+    return ok, detail
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from rawcooked_b200 import dist as D, ffv1, synth as S
+    from rawcooked_b200 import dist as D, ffv1
 
+    c = CONFIGS[args.config]
+    W, H = c["W"], c["H"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -219,14 +303,31 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    F = args.frames
-    layout = S.DPX_RGB_16_BE
-    fb = W * H * 6
+    F = args.frames if args.frames else c["frames"]
+    layout = c["layout"]
+    fb = frame_bytes(c)
 
-    enc = ffv1.FFV1Encoder(W, H, layout, slices=SLICES, max_frames=F, device=local)
-    d_frames = synth_frames_torch(F, 1000 + rank, dev)
+    enc = ffv1.FFV1Encoder(W, H, layout, slices=c["slices"], max_frames=F, device=local)
+    assert enc.frame_bytes == fb
+    d_frames = synth_frames_torch(c, F, 1000 + rank, dev)
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
+
+    # ---- FLAC leg of config 4: F / 24 s of 6-channel 96 kHz 24-bit audio per step, encoded inside the timed region
+    flac_enc = wav = None
+    flac_stats = None
+    if c["audio"]:
+        from rawcooked_b200 import flac as FL, synth as S
+        nsamp = F * AUDIO["rate"] // AUDIO["fps"]
+        pcm = S.wav_pcm(AUDIO["channels"], AUDIO["rate"], AUDIO["bits"], nsamp, seed=77)
+        wav = FL.pcm_to_wav_bytes(pcm, AUDIO["bits"])
+        flac_enc = FL.FLACEncoder(AUDIO["rate"], AUDIO["channels"], AUDIO["bits"], max_blocks=256, device=local)
+
+    def flac_step():
+        if flac_enc is None:
+            return 0
+        frames = flac_enc.encode(wav)
+        return sum(len(f) for f in frames)
 
     def barrier():
         torch.cuda.synchronize()
@@ -234,32 +335,56 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def gather_to_rank0():
-        """NCCL exchange of the encoded packets (rawcooked_b200/dist.py): lengths first, then every rank's arena to rank 0."""
-        arena, off, ln = enc.packets_device(F)
-        total = off[-1] + ln[-1]
-        mine = torch.as_tensor(_CudaBuf(arena, total), device=dev)
-        lens = torch.tensor(ln, dtype=torch.int64, device=dev)
-        got = D.gather_packets(mine, lens, rank, world, F)
-        return sum(int(a.numel()) for a, _ in got) if got is not None else total
+    # the packets of step i travel to rank 0 (NCCL over NVLink) on a side stream while step i+1 is being encoded: the arena
+    # of the step is first copied to one of two staging buffers (a device-to-device copy of ~4 GB)
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    staging = [None, None]
+    staged_ev = [None, None]
+    gathered = [0]
 
-    def step_device():
+    def gather_async(k):
+        arena, off, ln = enc.packets_device(F)               # waits for the encode of this step
+        total = off[-1] + ln[-1]
+        b = k & 1
+        if staged_ev[b] is not None:
+            staged_ev[b].synchronize()                        # the gather that last used this buffer is done
+        if staging[b] is None or staging[b].numel() < total:
+            staging[b] = torch.empty(int(total * 1.1) + 4096, dtype=torch.uint8, device=dev)
+        staging[b][:total].copy_(torch.as_tensor(_CudaBuf(arena, total), device=dev), non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        lens = torch.tensor(ln, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            got = D.gather_packets(staging[b][:total], lens, rank, world, F)
+            if got is not None:
+                gathered[0] = sum(int(a.numel()) for a, _ in got)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            staged_ev[b] = ev
+
+    def step_device(k):
         enc.encode_device(d_frames.data_ptr(), F, stream.cuda_stream)
+        if flac_enc is not None:
+            flac_step()
         if world > 1:
-            stream.synchronize()
-            gather_to_rank0()
+            gather_async(k)
 
     # ---- device-resident throughput (`value`)
-    for _ in range(args.warmup):
-        step_device()
+    for k in range(args.warmup):
+        step_device(k)
+    if side is not None:
+        side.synchronize()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
+    for k in range(args.steps):
+        step_device(k)
+    if side is not None:
+        stream.wait_stream(side)                              # the last gather ends inside the timed region
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -270,14 +395,35 @@ def run_b200(args):
     arena, off, ln = enc.packets_device(F)
     st = enc.stats()
     out_bytes = st["packet_bytes"]
+    dev_total = off[-1] + ln[-1]
+    dev_crc = zlib.crc32(torch.as_tensor(_CudaBuf(arena, dev_total), device=dev).cpu().numpy().tobytes())
 
-    # ---- end to end through the host-buffer C-ABI call: pinned host frames -> H2D -> encode -> D2H packets
+    # ---- end to end through the host-buffer C-ABI call: pinned host frames -> H2D -> encode -> D2H packets.
+    # N > 1: every rank's packets land in ONE host segment that rank 0 (the muxer's process) has mapped: each GPU writes its
+    # share over its own PCIe link (cudaHostRegister'ed POSIX shared memory), nothing funnels through rank 0's link.
     h_frames = torch.empty((F, fb), dtype=torch.uint8, pin_memory=True)
     h_frames.copy_(d_frames)
-    h_out = torch.empty(int(out_bytes * 1.05) + (1 << 20), dtype=torch.uint8, pin_memory=True)
+    cap = int(out_bytes * 1.05) + (1 << 20)
+    shm_path = "/dev/shm/b200_bench_%s" % os.environ.get("MASTER_PORT", str(os.getpid()))
+    if world > 1:
+        caps = torch.tensor([cap], dtype=torch.int64, device=dev)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX)
+        cap = (int(caps.item()) + 4095) & ~4095
+        if rank == 0:
+            with open(shm_path, "wb") as f:
+                f.truncate(cap * world)
+        dist.barrier()
+        fd = os.open(shm_path, os.O_RDWR)
+        mm = mmap.mmap(fd, cap * world)
+        seg = np.frombuffer(mm, dtype=np.uint8)
+        rc = torch.cuda.cudart().cudaHostRegister(seg.ctypes.data + rank * cap, cap, 0)
+        if int(rc) != 0:
+            raise SystemExit("bench.py: cudaHostRegister of the shared packet segment failed (%s)" % str(rc))
+        out_np = seg[rank * cap:(rank + 1) * cap]
+    else:
+        h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        out_np = h_out.numpy()
     h_np = h_frames.numpy()
-    out_np = h_out.numpy()
-    import ctypes as C
     L = ffv1.load_library()
     ptrs = (C.c_void_p * F)(*[h_np[i].ctypes.data for i in range(F)])
     offs = (C.c_size_t * F)()
@@ -287,13 +433,17 @@ def run_b200(args):
         if rc:
             raise RuntimeError(L.b200_last_error().decode())
 
+    flac_bytes = [0]
+
     def run_e2e(steps):
         """`steps` batches through the host entry points, two in flight: batch i+1 is submitted (H2D band by band + kernels)
         before the packets of batch i are fetched (D2H), so both PCIe directions hide behind the kernels."""
         ck(L.b200_ffv1_submit_host(enc._h, ptrs, F))
         for _ in range(steps - 1):
             ck(L.b200_ffv1_submit_host(enc._h, ptrs, F))
+            flac_bytes[0] = flac_step()
             ck(L.b200_ffv1_fetch_packets(enc._h, out_np.ctypes.data, out_np.size, offs, lens, F))
+        flac_bytes[0] = flac_step()
         ck(L.b200_ffv1_fetch_packets(enc._h, out_np.ctypes.data, out_np.size, offs, lens, F))
     run_e2e(max(2, args.warmup // 2))
     barrier()
@@ -306,6 +456,33 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    e2e_total = int(offs[F - 1] + lens[F - 1])
+    e2e_crc = zlib.crc32(out_np[:e2e_total].tobytes())
+
+    # rank 0 reads every rank's packets out of the shared host segment: the proof that the e2e result is in its memory
+    gather_ok = True
+    if world > 1:
+        mine = torch.tensor([e2e_total, e2e_crc], dtype=torch.int64, device=dev)
+        allv = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        if rank == 0:
+            for r in range(world):
+                n, crc = int(allv[r][0].item()), int(allv[r][1].item())
+                gather_ok = gather_ok and zlib.crc32(seg[r * cap:r * cap + n].tobytes()) == crc
+            gather_ok = gather_ok and gathered[0] > 0
+
+    # ---- check of what was timed: first / middle / last packet of the last e2e batch (host path through the C ABI) against
+    # the oracle and the reference decoder, and the device-resident batch byte-identical to it
+    check, check_detail = "skipped", None
+    if rank == 0 and not args.no_check:
+        idx = sorted(set([0, F // 2, F - 1]))[: max(1, args.check_frames)]
+        pays = [h_np[i] for i in idx]
+        pkts = [out_np[offs[i]:offs[i] + lens[i]] for i in idx]
+        ok, check_detail = check_packets(c, enc, pays, pkts)
+        ok = ok and dev_crc == e2e_crc and dev_total == e2e_total and gather_ok
+        check = "pass" if ok else "FAIL"
+        check_detail = {"frames": idx, "packets": check_detail, "device_batch_equals_host_batch": dev_crc == e2e_crc,
+                        "rank0_holds_all_ranks_packets": gather_ok if world > 1 else None}
 
     # ---- per-kernel device time of the same workload: one serial pass, every launch bracketed by CUDA events in the library
     enc.set_timing(True)
@@ -314,6 +491,18 @@ def run_b200(args):
     enc.packets_device(F)
     ts = enc.stats()
     enc.set_timing(False)
+    if flac_enc is not None and rank == 0:
+        # FLAC leg alone: whole-call time (H2D + k_flac + D2H) and the kernel share, SURVEY §8d: in = samples*ch*3 B, out = packet bytes
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            nbytes = flac_step()
+        torch.cuda.synchronize()
+        dtf = (time.perf_counter() - t0) / reps
+        flac_stats = {"in_bytes_per_step": int(wav.size), "out_bytes_per_step": int(nbytes), "ratio": nbytes / wav.size,
+                      "MB_per_s": wav.size / dtf / 1e6, "x_realtime": (wav.size / (AUDIO["rate"] * AUDIO["channels"] * 3)) / dtf,
+                      "block_size": flac_enc.block_size, "what": "b200_flac_encode_host: host PCM -> FLAC frames in host memory"}
 
     if rank == 0:
         pix_step = F * W * H * world
@@ -338,14 +527,23 @@ def run_b200(args):
             pass
         cpu = None
         if world == 1 and not args.no_cpu:
-            c = cpu_reference_run(args.cpu_seconds)
-            cpu = {"value": c["value"], "unit": "MPix/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
+            ref = CpuReference(c)
+            t_cal = ref.run(ref.workers)
+            n = max(ref.workers, int(args.cpu_seconds * ref.workers / max(t_cal, 1e-3)))
+            n -= n % ref.workers
+            dtc = ref.run(n)
+            cpu = {"value": n * W * H / dtc / 1e6, "unit": "MPix/s", "cores": ref.workers, "kind": ref.kind, "sample": ref.describe(n, dtc)}
+            ref.close()
         line = {
-            "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(c), "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic", "config": workload_config(F, world),
+            "dtype": "int32", "data": "synthetic", "config": workload_config(c, F, world),
+            "check": check, "check_detail": check_detail,
             "e2e": {"value": e2e, "unit": "MPix/s", "h2d_bytes_per_step": F * fb * world, "d2h_bytes_per_step": int(out_bytes) * world,
-                    "api": "b200_ffv1_submit_host + b200_ffv1_fetch_packets, two batches in flight (pinned host frames -> packets in pinned host memory; every step's frames cross PCIe inside the timed region, H2D band by band, D2H of batch i during batch i+1)", "fps": e2e * 1e6 / (W * H)},
+                    "api": "b200_ffv1_submit_host + b200_ffv1_fetch_packets, two batches in flight (pinned host frames -> packets in pinned host memory; "
+                           "every step's frames cross PCIe inside the timed region, H2D band by band, D2H of batch i during batch i+1)"
+                           + ("; all ranks fetch into one host segment mapped by rank 0 (each GPU over its own PCIe link)" if world > 1 else ""),
+                    "fps": e2e * 1e6 / (W * H)},
             "gpu_launches": int(st["launches"]) * args.steps * world,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -359,11 +557,22 @@ def run_b200(args):
             "fps": value * 1e6 / (W * H), "bins_per_s": st["bins"] * args.steps * world / (dev_ms / 1e3),
             "bins_per_sample": st["bins"] / st["samples"], "compression_ratio": out_bytes / (F * fb),
         }
+        if flac_stats is not None:
+            line["flac"] = flac_stats
         print(json.dumps(line), flush=True)
     enc.close()
+    if flac_enc is not None:
+        flac_enc.close()
     if world > 1:
         dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
         dist.destroy_process_group()
+    if rank == 0 and check == "FAIL":
+        sys.exit(3)
 
 
 def main():
@@ -371,12 +580,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=int(os.environ.get("B200_BENCH_FRAMES", "128")), help="frames per step per GPU")
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS), help="BASELINE.json configuration (counted from 1)")
+    ap.add_argument("--frames", type=int, default=int(os.environ.get("B200_BENCH_FRAMES", "0")), help="frames per step per GPU (default: per config)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle / reference-decoder check of the timed packets")
+    ap.add_argument("--check-frames", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
+        if not args.frames:
+            args.frames = CONFIGS[args.config]["frames"]
         run_reference(args)
     else:
         run_b200(args)

@@ -121,6 +121,9 @@ int b200_ffv1_submit_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int3
 int b200_ffv1_encode_device(b200_ffv1_enc* enc, const void* d_frames, int32_t n_frames, void* stream);
 int b200_ffv1_packets_device(b200_ffv1_enc* enc, const void** d_arena, size_t* out_off, size_t* out_len, int32_t n_frames);
 int b200_ffv1_fetch_packets(b200_ffv1_enc* enc, uint8_t* out, size_t out_cap, size_t* out_off, size_t* out_len, int32_t n_frames);
+/* Waits for the OLDEST batch in flight and reports its packet layout (offsets / lengths in the arena, total bytes) without
+ * collecting it: the caller can size (and pin) its output buffer before b200_ffv1_fetch_packets(). */
+int b200_ffv1_packet_sizes(b200_ffv1_enc* enc, size_t* out_off, size_t* out_len, int32_t n_frames, size_t* total_bytes);
 
 /* Counters of the last encode call: [0] kernels launched, [1] range-coder bins coded,
  * [2] samples coded, [3] bytes of packets produced; plus, when timing is enabled with b200_ffv1_set_timing()

@@ -86,16 +86,148 @@ static int utf8_put(bitw* w, uint64_t v)
     return n;
 }
 
-/* subframe of one channel: x[0..n) (already signed, bps bits) */
-static void encode_subframe(bitw* w, const int32_t* x, int n, int bps)
+/* ---- partitioned Rice: exact search of the partition order for the residual u[pred_order..n) (zig-zag folded) ---- */
+typedef struct { uint64_t cost; int p, rice2; uint8_t k[256]; } rice_choice;
+
+static void rice_search(const uint32_t* u, int n, int pred_order, rice_choice* best)
 {
+    int pmax = 0;
+    while (pmax < 8 && (n % (2 << pmax)) == 0 && (n >> (pmax + 1)) > pred_order) pmax++;
+    best->cost = UINT64_MAX; best->p = 0; best->rice2 = 0;
+    for (int p = 0; p <= pmax; p++) {
+        const int np = 1 << p, m = n >> p;
+        uint64_t cost = 0; int anybig = 0; uint8_t ks[256];
+        for (int j = 0; j < np; j++) {
+            const int b = j ? j * m : pred_order, end = (j + 1) * m, cnt = end - b;
+            uint64_t S = 0;
+            for (int i = b; i < end; i++) S += u[i];
+            int k = 0;
+            while (k < 30 && ((uint64_t)cnt << (k + 1)) <= S) k++;
+            uint64_t bits = (uint64_t)cnt * (uint64_t)(k + 1);
+            for (int i = b; i < end; i++) bits += u[i] >> k;
+            ks[j] = (uint8_t)k; cost += bits; if (k > 14) anybig = 1;
+        }
+        cost += (uint64_t)np * (anybig ? 5 : 4);
+        if (cost < best->cost) { best->cost = cost; best->p = p; best->rice2 = anybig; memcpy(best->k, ks, (size_t)np); }
+    }
+}
+
+static void rice_put(bitw* w, const uint32_t* u, int n, int pred_order, const rice_choice* c)
+{
+    bw_put(w, c->rice2 ? 1 : 0, 2);
+    bw_put(w, (uint32_t)c->p, 4);
+    const int np = 1 << c->p, m = n >> c->p;
+    for (int j = 0; j < np; j++) {
+        const int b = j ? j * m : pred_order, end = (j + 1) * m, k = c->k[j];
+        bw_put(w, (uint32_t)k, c->rice2 ? 5 : 4);
+        for (int i = b; i < end; i++) {
+            bw_zeros(w, u[i] >> k);
+            bw_put(w, 1, 1);
+            if (k) bw_put(w, u[i] & ((1u << k) - 1), k);
+        }
+    }
+}
+
+/* ---- LPC analysis. What the decoder fixes is the predictor arithmetic
+ * (FLAC__lpc_restore_signal / _wide, lpc.c:784-1100: data[i] = residual[i] + (int32)(sum(qlp[j] * data[i-j-1]) >> shift), 64-bit
+ * sum whenever bps + precision + ilog2(order) > 32, stream_decoder.c:2710-2716) and the subframe syntax
+ * (read_subframe_lpc_, stream_decoder.c:2627-2722). The analysis is the encoder's own business; this one is built to give the
+ * same bits on a CPU and on a GPU: integer Welch window, exact 64-bit integer autocorrelation, Levinson-Durbin in IEEE double
+ * with every operation a separate correctly rounded +, -, *, / (no fused multiply-add: compile with -ffp-contract=off),
+ * coefficient quantisation as in FLAC__lpc_quantize_coefficients (lpc.c:166-266: 15-bit precision, error feedback), orders
+ * 1..8 like ffmpeg's level 5, the order picked by an integer estimate of the Rice-coded size. */
+#define LPC_MAX_ORDER 8
+#define LPC_PRECISION 15
+
+static int lpc_window15(int i, int n) { return (int)((4 * (int64_t)i * (int64_t)(n - 1 - i) * 32767) / ((int64_t)(n - 1) * (int64_t)(n - 1))); }
+
+typedef struct { int order, shift; int32_t q[LPC_MAX_ORDER]; } lpc_params;
+
+/* quantised predictors of orders 1..LPC_MAX_ORDER for x[0..n); valid[m-1] = 0 when order m is unusable. Returns 0 if the block
+ * has no energy (nothing to analyse). */
+static int lpc_analyse(const int32_t* x, int n, lpc_params out[LPC_MAX_ORDER], int valid[LPC_MAX_ORDER])
+{
+    int64_t ac[LPC_MAX_ORDER + 1];
+    for (int l = 0; l <= LPC_MAX_ORDER; l++) ac[l] = 0;
+    int32_t* xw = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    for (int i = 0; i < n; i++) xw[i] = (int32_t)(((int64_t)x[i] * lpc_window15(i, n)) >> 15);
+    for (int l = 0; l <= LPC_MAX_ORDER; l++)
+        for (int i = l; i < n; i++) ac[l] += (int64_t)xw[i] * xw[i - l];
+    free(xw);
+    for (int m = 0; m < LPC_MAX_ORDER; m++) valid[m] = 0;
+    if (ac[0] <= 0) return 0;
+    double R[LPC_MAX_ORDER + 1], a[LPC_MAX_ORDER], prev[LPC_MAX_ORDER];
+    for (int l = 0; l <= LPC_MAX_ORDER; l++) R[l] = (double)ac[l];
+    double E = R[0];
+    for (int m = 1; m <= LPC_MAX_ORDER; m++) {
+        double acc = R[m];
+        for (int j = 1; j < m; j++) { const double t = prev[j - 1] * R[m - j]; acc = acc - t; }
+        if (!(E > 0.0)) break;
+        const double k = acc / E;
+        a[m - 1] = k;
+        for (int j = 1; j < m; j++) { const double t = k * prev[m - 1 - j]; a[j - 1] = prev[j - 1] - t; }
+        { const double t = k * k; const double u = 1.0 - t; E = E * u; }
+        for (int j = 0; j < m; j++) prev[j] = a[j];
+        /* quantise order m */
+        double cmax = 0.0;
+        for (int j = 0; j < m; j++) { const double d = a[j] < 0.0 ? -a[j] : a[j]; if (d > cmax) cmax = d; }
+        if (!(cmax > 0.0) || !(cmax < 1.0e9)) continue;
+        uint64_t bits; memcpy(&bits, &cmax, 8);
+        const int e = (int)((bits >> 52) & 0x7FF) - 1022;             /* cmax = f * 2^e, f in [0.5, 1): frexp's exponent */
+        int shift = LPC_PRECISION - 1 - e;
+        if (shift > 15) shift = 15;
+        if (shift < 0) continue;
+        const int64_t qmax = (1 << (LPC_PRECISION - 1)) - 1, qmin = -(1 << (LPC_PRECISION - 1));
+        const double scale = (double)(1 << shift);
+        double err = 0.0;
+        lpc_params* P = &out[m - 1];
+        P->order = m; P->shift = shift;
+        for (int j = 0; j < m; j++) {
+            const double t = a[j] * scale;
+            err = err + t;
+            const double r = err >= 0.0 ? err + 0.5 : err - 0.5;
+            int64_t q = (int64_t)r;                                   /* truncation: round half away from zero */
+            if (q > qmax) q = qmax;
+            if (q < qmin) q = qmin;
+            err = err - (double)q;
+            P->q[j] = (int32_t)q;
+        }
+        valid[m - 1] = 1;
+    }
+    return 1;
+}
+
+/* residual of predictor P over x[P->order..n) into u (zig-zag); returns 0 if a residual does not fit 31 bits. sum_u = sum of u. */
+static int lpc_residual(const int32_t* x, int n, const lpc_params* P, uint32_t* u, uint64_t* sum_u)
+{
+    uint64_t S = 0;
+    for (int i = P->order; i < n; i++) {
+        int64_t sum = 0;
+        for (int j = 0; j < P->order; j++) sum += (int64_t)P->q[j] * (int64_t)x[i - 1 - j];
+        const int32_t pred = (int32_t)(sum >> P->shift);
+        const int64_t e = (int64_t)x[i] - (int64_t)pred;
+        if (e > 0x3FFFFFFF || e < -0x40000000) return 0;
+        const int32_t e32 = (int32_t)e;
+        const uint32_t z = ((uint32_t)e32 << 1) ^ (uint32_t)(e32 >> 31);
+        if (u) u[i] = z;
+        S += z;
+    }
+    *sum_u = S;
+    return 1;
+}
+
+/* subframe of one channel: x[0..n) (already signed, bps bits) */
+static void encode_subframe(bitw* w, const int32_t* x, int n, int bps, int use_lpc)
+{
+    const uint32_t vmask = bps == 32 ? 0xFFFFFFFFu : ((1u << bps) - 1);
     int constant = 1;
     for (int i = 1; i < n; i++) if (x[i] != x[0]) { constant = 0; break; }
-    if (constant) { bw_put(w, 0x00, 8); bw_put(w, (uint32_t)x[0] & (bps == 32 ? 0xFFFFFFFFu : ((1u << bps) - 1)), bps); return; }
-    int order = -1, best_p = 0, rice2 = 0;
-    uint64_t best_cost = 0;
-    int32_t* e = NULL; uint32_t* u = NULL;
-    uint8_t kbest[256];
+    if (constant) { bw_put(w, 0x00, 8); bw_put(w, (uint32_t)x[0] & vmask, bps); return; }
+    int order = -1;
+    rice_choice fixed_c, lpc_c;
+    uint64_t fixed_bits = UINT64_MAX, lpc_bits = UINT64_MAX;
+    lpc_params lp; lp.order = 0; lp.shift = 0;
+    uint32_t* u = NULL;
     if (n >= 16) {
         uint64_t sum[5] = {0, 0, 0, 0, 0};
         for (int i = 4; i < n; i++) {
@@ -109,7 +241,32 @@ static void encode_subframe(bitw* w, const int32_t* x, int n, int bps)
         }
         order = 0;
         for (int o = 1; o <= 4; o++) if (sum[o] < sum[order]) order = o;
-        e = (int32_t*)malloc(sizeof(int32_t) * (size_t)n); u = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
+        u = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
+        /* ---- LPC candidate: the order whose estimated size is smallest, then its exact size */
+        if (use_lpc && n > 2 * LPC_MAX_ORDER) {
+            lpc_params cand[LPC_MAX_ORDER]; int valid[LPC_MAX_ORDER];
+            if (lpc_analyse(x, n, cand, valid)) {
+                uint64_t best_est = UINT64_MAX; int best_m = 0;
+                for (int m = 1; m <= LPC_MAX_ORDER; m++) {
+                    if (!valid[m - 1]) continue;
+                    uint64_t S;
+                    if (!lpc_residual(x, n, &cand[m - 1], NULL, &S)) continue;
+                    const uint64_t cnt = (uint64_t)(n - m);
+                    int k = 0;
+                    while (k < 30 && (cnt << (k + 1)) <= S) k++;
+                    const uint64_t est = cnt * (uint64_t)(k + 1) + (S >> k) + (uint64_t)m * (uint64_t)(bps + LPC_PRECISION);
+                    if (est < best_est) { best_est = est; best_m = m; }
+                }
+                if (best_m) {
+                    lp = cand[best_m - 1];
+                    uint64_t S;
+                    lpc_residual(x, n, &lp, u, &S);
+                    rice_search(u, n, lp.order, &lpc_c);
+                    lpc_bits = 8 + (uint64_t)lp.order * bps + 4 + 5 + (uint64_t)lp.order * LPC_PRECISION + 6 + lpc_c.cost;
+                }
+            }
+        }
+        /* ---- fixed candidate */
         for (int i = order; i < n; i++) {
             int64_t r;
             switch (order) {
@@ -119,56 +276,47 @@ static void encode_subframe(bitw* w, const int32_t* x, int n, int bps)
             case 3: r = (int64_t)x[i] - 3 * (int64_t)x[i - 1] + 3 * (int64_t)x[i - 2] - x[i - 3]; break;
             default: r = (int64_t)x[i] - 4 * (int64_t)x[i - 1] + 6 * (int64_t)x[i - 2] - 4 * (int64_t)x[i - 3] + x[i - 4]; break;
             }
-            e[i] = (int32_t)r;
-            u[i] = ((uint32_t)e[i] << 1) ^ (uint32_t)(e[i] >> 31);
+            const int32_t e = (int32_t)r;
+            u[i] = ((uint32_t)e << 1) ^ (uint32_t)(e >> 31);
         }
-        int pmax = 0;
-        while (pmax < 8 && (n % (2 << pmax)) == 0 && (n >> (pmax + 1)) > order) pmax++;
-        best_cost = UINT64_MAX;
-        for (int p = 0; p <= pmax; p++) {
-            const int np = 1 << p, m = n >> p;
-            uint64_t cost = 0; int anybig = 0; uint8_t ks[256];
-            for (int j = 0; j < np; j++) {
-                const int b = j ? j * m : order, end = (j + 1) * m, cnt = end - b;
-                uint64_t S = 0;
-                for (int i = b; i < end; i++) S += u[i];
-                int k = 0;
-                while (k < 30 && ((uint64_t)cnt << (k + 1)) <= S) k++;
-                uint64_t bits = (uint64_t)cnt * (uint64_t)(k + 1);
-                for (int i = b; i < end; i++) bits += u[i] >> k;
-                ks[j] = (uint8_t)k; cost += bits; if (k > 14) anybig = 1;
-            }
-            cost += (uint64_t)np * (anybig ? 5 : 4);
-            if (cost < best_cost) { best_cost = cost; best_p = p; rice2 = anybig; memcpy(kbest, ks, (size_t)np); }
-        }
+        rice_search(u, n, order, &fixed_c);
+        fixed_bits = 8 + (uint64_t)order * bps + 6 + fixed_c.cost;
     }
-    if (order < 0 || 8 + (uint64_t)order * bps + 6 + best_cost >= 8 + (uint64_t)n * bps) {
+    const uint64_t verbatim_bits = 8 + (uint64_t)n * bps;
+    if (lpc_bits < fixed_bits && lpc_bits < verbatim_bits) {
+        uint64_t S;
+        lpc_residual(x, n, &lp, u, &S);
+        bw_put(w, (uint32_t)((32 | (lp.order - 1)) << 1), 8);   /* LPC: 0 | 1ooooo | 0 (read_subframe_, stream_decoder.c:2521-2527) */
+        for (int i = 0; i < lp.order; i++) bw_put(w, (uint32_t)x[i] & vmask, bps);
+        bw_put(w, LPC_PRECISION - 1, 4);
+        bw_put(w, (uint32_t)lp.shift, 5);
+        for (int j = 0; j < lp.order; j++) bw_put(w, (uint32_t)lp.q[j] & ((1u << LPC_PRECISION) - 1), LPC_PRECISION);
+        rice_put(w, u, n, lp.order, &lpc_c);
+    } else if (order < 0 || fixed_bits >= verbatim_bits) {
         bw_put(w, 0x02, 8);                                   /* VERBATIM: 0 | 000001 | 0 */
-        for (int i = 0; i < n; i++) bw_put(w, (uint32_t)x[i] & ((1u << bps) - 1), bps);
+        for (int i = 0; i < n; i++) bw_put(w, (uint32_t)x[i] & vmask, bps);
     } else {
         bw_put(w, (uint32_t)((8 | order) << 1), 8);           /* FIXED: 0 | 001ooo | 0 */
-        for (int i = 0; i < order; i++) bw_put(w, (uint32_t)x[i] & ((1u << bps) - 1), bps);
-        bw_put(w, rice2 ? 1 : 0, 2);
-        bw_put(w, (uint32_t)best_p, 4);
-        const int np = 1 << best_p, m = n >> best_p;
-        for (int j = 0; j < np; j++) {
-            const int b = j ? j * m : order, end = (j + 1) * m, k = kbest[j];
-            bw_put(w, (uint32_t)k, rice2 ? 5 : 4);
-            for (int i = b; i < end; i++) {
-                bw_zeros(w, u[i] >> k);
-                bw_put(w, 1, 1);
-                if (k) bw_put(w, u[i] & ((1u << k) - 1), k);
-            }
-        }
+        for (int i = 0; i < order; i++) bw_put(w, (uint32_t)x[i] & vmask, bps);
+        rice_put(w, u, n, order, &fixed_c);
     }
-    free(e); free(u);
+    free(u);
 }
 
 /* one frame: pcm = interleaved int32 [n][channels]; returns bytes written (0 on overflow) */
+size_t flaco_encode_frame2(const int32_t* pcm, int n, int channels, int bps, int sample_rate, int use_lpc,
+                           uint64_t frame_number, uint8_t* out, size_t cap);
 size_t flaco_encode_frame(const int32_t* pcm, int n, int channels, int bps, int sample_rate, int blocksize_nominal,
                           uint64_t frame_number, uint8_t* out, size_t cap)
 {
     (void)blocksize_nominal;
+    return flaco_encode_frame2(pcm, n, channels, bps, sample_rate, 1, frame_number, out, cap);
+}
+
+/* use_lpc = 0: fixed predictors only (`compression_level` below 3 in ffmpeg's terms) */
+size_t flaco_encode_frame2(const int32_t* pcm, int n, int channels, int bps, int sample_rate, int use_lpc,
+                           uint64_t frame_number, uint8_t* out, size_t cap)
+{
     memset(out, 0, cap);
     bitw w = {out, cap, 0, 0};
     int bs_extra, sr_extra; uint32_t sr_val;
@@ -183,7 +331,7 @@ size_t flaco_encode_frame(const int32_t* pcm, int n, int channels, int bps, int 
     int32_t* x = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
     for (int c = 0; c < channels; c++) {
         for (int i = 0; i < n; i++) x[i] = pcm[(size_t)i * channels + c];
-        encode_subframe(&w, x, n, bps);
+        encode_subframe(&w, x, n, bps, use_lpc);
     }
     free(x);
     if (w.bitpos & 7) bw_zeros(&w, 8 - (w.bitpos & 7));

@@ -17,7 +17,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -97,6 +99,214 @@ int fail(const std::string& msg, int code = 1) {
 
 }  // namespace
 
+
+namespace {
+
+// One worker per GPU. Batch k (frames [k*B, k*B + B)) belongs to worker k % G, which keeps two of its batches in flight
+// through b200_ffv1_submit_host: while batch j is being coded, the files of batch j+1 are read into the other pinned input
+// buffer and the packets of batch j-1 cross PCIe into a pinned output buffer. The muxer (the calling thread) takes the
+// batches in order and hands the packets to the Matroska writer's pwrite pool straight from those buffers.
+struct Batch {
+    size_t f0 = 0, n = 0;
+    uint8_t* data = nullptr;                  // pinned output buffer of the owning worker
+    std::vector<size_t> off, len;
+    bool ready = false, consumed = false;
+    std::string err;
+};
+
+struct VideoPipeline {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Batch> batches;
+    bool abort = false;
+};
+
+struct PinnedBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t need) {
+        if (need <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = need + (need >> 3);
+        if (cudaHostAlloc((void**)&p, want, cudaHostAllocDefault) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+template <class FlushAudio>
+int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vector<int>& devices, int frames_in_flight, unsigned nthreads,
+                        int slices, int context, int slicecrc, b200::MkvWriter& mux, FlushAudio& flush_audio_until, PhaseClock& pc, std::string* err) {
+    const size_t fb = b200_ffv1_frame_bytes(v.info.width, v.info.height, v.info.layout);
+    const size_t N = v.files.size();
+    const size_t B = std::min<size_t>((size_t)frames_in_flight, N);
+    const size_t nbatch = (N + B - 1) / B;
+    const size_t G = std::max<size_t>(1, std::min(devices.size(), nbatch));
+    VideoPipeline P;
+    P.batches.resize(nbatch);
+    for (size_t k = 0; k < nbatch; k++) { P.batches[k].f0 = k * B; P.batches[k].n = std::min(B, N - k * B); }
+    const unsigned nread = std::max(1u, std::min(nthreads / (unsigned)G, 32u));
+
+    // reads frames [f0, f0 + n) into dst (pread straight into pinned memory; one header parse per file because the payload
+    // offset may differ from frame to frame); returns "" or the first error
+    auto read_batch = [&](size_t f0, size_t n, uint8_t* dst) -> std::string {
+        std::vector<std::string> errs(nread);
+        auto work = [&](unsigned t) {
+            std::vector<uint8_t> head(65536);
+            for (size_t k = t; k < n && errs[t].empty(); k += nread) {
+                const std::string& path = v.files[f0 + k];
+                const int fd = open(path.c_str(), O_RDONLY);
+                if (fd < 0) { errs[t] = "cannot open " + path; return; }
+                b200::ImageInfo fi = v.info;
+                if (f0 + k > 0) {
+                    const ssize_t hn = pread(fd, head.data(), head.size(), 0);
+                    std::string e;
+                    const bool ok = v.kind == 'd' ? b200::parse_dpx(head.data(), hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &e)
+                                                  : b200::parse_tiff(head.data(), hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &e);
+                    if (!ok || fi.width != v.info.width || fi.height != v.info.height || fi.layout != v.info.layout) {
+                        close(fd);
+                        errs[t] = path + ": " + (ok ? std::string("geometry differs from the first frame") : e);
+                        return;
+                    }
+                }
+                if (!read_at(fd, dst + k * fb, fb, fi.data_offset)) { close(fd); errs[t] = "cannot read " + path; return; }
+                close(fd);
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nread; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        for (auto& e : errs) if (!e.empty()) return e;
+        return "";
+    };
+
+    auto worker = [&](size_t w, b200_ffv1_enc* E) {
+        const int device = devices[w];
+        std::string werr;
+        auto fail_all = [&](const std::string& m) {
+            std::lock_guard<std::mutex> lk(P.mu);
+            for (size_t k = w; k < nbatch; k += G) if (!P.batches[k].ready) { P.batches[k].err = m; P.batches[k].ready = true; }
+            P.abort = true;
+            P.cv.notify_all();
+        };
+        cudaSetDevice(device);
+        if (!E) {
+            b200_ffv1_cfg cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.width = v.info.width; cfg.height = v.info.height; cfg.layout = v.info.layout;
+            cfg.slices = slices; cfg.context = context; cfg.coder = 1; cfg.slicecrc = slicecrc;
+            cfg.max_frames = (int32_t)B; cfg.device = device;
+            if (b200_ffv1_open(&cfg, &E)) { fail_all(std::string("ffv1: ") + b200_last_error()); return; }
+        }
+        PinnedBuf in[2], out[2];
+        // pinning is slow (a few GB/s): the second input buffer and the output buffers are pinned in the background while
+        // the first batch is read and coded
+        bool bg_ok = true;
+        std::thread bg;
+        const size_t out_guess = fb * B - (fb * B >> 2);
+        if (!in[0].ensure(fb * B)) { b200_ffv1_close(E); fail_all("cannot allocate pinned host buffers"); return; }
+        bg = std::thread([&] {
+            cudaSetDevice(device);
+            bg_ok = out[0].ensure(out_guess);
+            if ((nbatch + G - 1 - w) / G > 1) bg_ok = bg_ok && in[1].ensure(fb * B) && out[1].ensure(out_guess);
+        });
+        struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } guard{bg};
+        std::vector<const uint8_t*> ptrs(B);
+        size_t j = 0;
+        long prev = -1;                                           // my previous batch: submitted, not yet fetched
+        auto fetch = [&](size_t k, size_t jj) -> bool {
+            Batch& bt = P.batches[k];
+            bt.off.resize(bt.n); bt.len.resize(bt.n);
+            size_t total = 0;
+            if (b200_ffv1_packet_sizes(E, bt.off.data(), bt.len.data(), (int32_t)bt.n, &total)) { werr = std::string("ffv1 encode: ") + b200_last_error(); return false; }
+            PinnedBuf& o = out[jj & 1];
+            if (jj >= 2) {                                        // the muxer must be done with the batch that used this buffer
+                std::unique_lock<std::mutex> lk(P.mu);
+                P.cv.wait(lk, [&] { return P.batches[k - 2 * G].consumed || P.abort; });
+                if (P.abort) { werr = "aborted"; return false; }
+            }
+            if (bg.joinable()) bg.join();
+            if (!bg_ok || !o.ensure(total)) { werr = "cannot allocate pinned host buffers"; return false; }
+            if (b200_ffv1_fetch_packets(E, o.p, o.cap, bt.off.data(), bt.len.data(), (int32_t)bt.n)) { werr = std::string("ffv1 fetch: ") + b200_last_error(); return false; }
+            {
+                std::lock_guard<std::mutex> lk(P.mu);
+                bt.data = o.p;
+                bt.ready = true;
+            }
+            P.cv.notify_all();
+            return true;
+        };
+        for (size_t k = w; k < nbatch; k += G, j++) {
+            Batch& bt = P.batches[k];
+            if (j == 1 && bg.joinable()) bg.join();
+            if (j >= 1 && !bg_ok) { werr = "cannot allocate pinned host buffers"; break; }
+            const std::string rerr = read_batch(bt.f0, bt.n, in[j & 1].p);
+            if (!rerr.empty()) { werr = rerr; break; }
+            for (size_t i = 0; i < bt.n; i++) ptrs[i] = in[j & 1].p + i * fb;
+            if (b200_ffv1_submit_host(E, ptrs.data(), (int32_t)bt.n)) { werr = std::string("ffv1 encode: ") + b200_last_error(); break; }
+            if (prev >= 0 && !fetch((size_t)prev, j - 1)) break;
+            prev = (long)k;
+            {
+                std::lock_guard<std::mutex> lk(P.mu);
+                if (P.abort) { werr = "aborted"; break; }
+            }
+        }
+        if (werr.empty() && prev >= 0) fetch((size_t)prev, j - 1);
+        if (!werr.empty()) fail_all(werr);
+        // the pinned output buffers must outlive the muxer's use of them
+        {
+            std::unique_lock<std::mutex> lk(P.mu);
+            P.cv.wait(lk, [&] {
+                if (P.abort) return true;
+                for (size_t k = w; k < nbatch; k += G) if (!P.batches[k].consumed) return false;
+                return true;
+            });
+        }
+        if (bg.joinable()) bg.join();
+        b200_ffv1_close(E);
+    };
+
+    std::vector<std::thread> workers;
+    for (size_t w = 0; w < G; w++) workers.emplace_back(worker, w, w == 0 ? first_enc : nullptr);
+    pc.mark("workers started");
+    int rc = 0;
+    for (size_t k = 0; k < nbatch && !rc; k++) {
+        Batch& bt = P.batches[k];
+        {
+            std::unique_lock<std::mutex> lk(P.mu);
+            P.cv.wait(lk, [&] { return bt.ready; });
+        }
+        pc.mark("wait for batch");
+        if (!bt.err.empty()) { *err = bt.err; rc = 1; break; }
+        bool ok = true;
+        for (size_t i = 0; i < bt.n && ok; i++) {
+            const int64_t t_ms = (int64_t)std::llround(1000.0 * (double)(bt.f0 + i) / v.fps);
+            ok = flush_audio_until(t_ms) && mux.write_block(v.track, t_ms, bt.data + bt.off[i], bt.len[i]);
+        }
+        ok = ok && mux.sync();                                    // the packets have left the pinned buffer
+        pc.mark("mux write (batch)");
+        if (!ok) { *err = mux.error(); rc = B200_ERR_IO; }
+        {
+            std::lock_guard<std::mutex> lk(P.mu);
+            bt.consumed = true;
+            if (rc) P.abort = true;
+        }
+        P.cv.notify_all();
+    }
+    if (rc) {
+        std::lock_guard<std::mutex> lk(P.mu);
+        P.abort = true;
+        P.cv.notify_all();
+    }
+    for (auto& t : workers) t.join();
+    return rc;
+}
+
+}  // namespace
+
 int b200_flac_encode_file_to_mux(const std::string& path, const b200::WavInfo& wi, int track, int device,
                                  std::vector<uint8_t>* codec_private, std::vector<std::pair<int64_t, std::vector<uint8_t>>>* packets,
                                  std::string* err);   // flac_host.cpp
@@ -155,8 +365,27 @@ extern "C" int b200enc_main(int argc, char** argv) {
     const int slicecrc = outopt.count("-slicecrc") ? atoi(outopt["-slicecrc"].c_str()) : 1;
     const int slices = outopt.count("-slices") ? atoi(outopt["-slices"].c_str()) : 0;
     const bool audio_flac = !(outopt.count("-c:a") && outopt["-c:a"] == "copy");
-    int device = 0;
-    if (const char* e = getenv("B200_DEVICE")) device = atoi(e);
+    // GPUs: B200_DEVICES="0,1,..." (an ordinal may repeat: two workers on one GPU), else B200_DEVICE=k, else every visible device
+    std::vector<int> devices;
+    if (const char* e = getenv("B200_DEVICES")) {
+        for (const char* q = e; *q;) {
+            char* endp = nullptr;
+            const long d = strtol(q, &endp, 10);
+            if (endp == q) break;
+            devices.push_back((int)d);
+            q = *endp == ',' ? endp + 1 : endp;
+        }
+    } else if (const char* e1 = getenv("B200_DEVICE")) {
+        devices.push_back(atoi(e1));
+    } else {
+        int nd = 0;
+        if (cudaGetDeviceCount(&nd) == cudaSuccess) for (int d = 0; d < nd; d++) devices.push_back(d);
+    }
+    if (devices.empty()) devices.push_back(0);
+    const int device = devices[0];
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (outopt.count("-threads") && atoi(outopt["-threads"].c_str()) > 0) nthreads = (unsigned)atoi(outopt["-threads"].c_str());
+    nthreads = std::max(1u, nthreads);
 
     // ---- classify the inputs
     std::vector<VideoStream> videos;
@@ -275,7 +504,7 @@ extern "C" int b200enc_main(int argc, char** argv) {
     b200::MkvWriter mux;
     if (!mux.open(out_path, tracks, atts, duration_ms)) { cleanup(); return fail(mux.error(), B200_ERR_IO); }
 
-    // ---- encode: video in batches through the GPU, audio packets interleaved by timestamp
+    // ---- encode: video in batches through the GPU(s), audio packets interleaved by timestamp
     std::vector<size_t> apos(audios.size(), 0);
     auto flush_audio_until = [&](int64_t t_ms) -> bool {
         for (size_t k = 0; k < audios.size(); k++)
@@ -286,126 +515,10 @@ extern "C" int b200enc_main(int argc, char** argv) {
         return true;
     };
     for (size_t vi = 0; vi < videos.size(); vi++) {
-        VideoStream& v = videos[vi];
-        b200_ffv1_enc* E = encs[vi];
-        const size_t fb = b200_ffv1_frame_bytes(v.info.width, v.info.height, v.info.layout);
-        const size_t B = std::min<size_t>((size_t)frames_in_flight, v.files.size());
-        // Source-file ingest at rate: the payloads of a batch are read by `nread` threads (pread straight into pinned
-        // memory, one header parse per file because the payload offset may differ from frame to frame), and the NEXT batch is
-        // read while the GPU encodes the current one (two pinned input buffers).
-        uint8_t* h_in[2] = {nullptr, nullptr};
-        // packets leave the device one by one through a two-slot pinned ring (a packet is tens of MB; pinning a buffer for
-        // a whole batch of worst-case packets would take longer than encoding it)
-        uint8_t* h_ring[2] = {nullptr, nullptr};
-        size_t ring_cap = std::max<size_t>(fb + (fb >> 2), (size_t)1 << 20);
-        cudaStream_t cs = nullptr;
-        cudaEvent_t cev[2] = {nullptr, nullptr};
-        const bool two = v.files.size() > B;
-        // pinning memory is slow (a few GB/s): the second input buffer is pinned in the background while the first batch is
-        // read and encoded
-        bool in1_ok = true;
-        std::thread pin1;
-        if (two) pin1 = std::thread([&] { cudaSetDevice(device); in1_ok = cudaHostAlloc((void**)&h_in[1], fb * B, cudaHostAllocDefault) == cudaSuccess; });
-        if (cudaHostAlloc((void**)&h_in[0], fb * B, cudaHostAllocDefault) != cudaSuccess ||
-            cudaHostAlloc((void**)&h_ring[0], ring_cap, cudaHostAllocDefault) != cudaSuccess ||
-            cudaHostAlloc((void**)&h_ring[1], ring_cap, cudaHostAllocDefault) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&cev[0], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&cev[1], cudaEventDisableTiming) != cudaSuccess) {
-            if (pin1.joinable()) pin1.join();
-            cleanup(); return fail("cannot allocate pinned host buffers");
-        }
-        unsigned nread = std::thread::hardware_concurrency();
-        if (outopt.count("-threads") && atoi(outopt["-threads"].c_str()) > 0) nread = (unsigned)atoi(outopt["-threads"].c_str());
-        nread = std::max(1u, std::min(nread, 32u));
-        // reads frames [f0, f0 + n) into dst; returns "" or the first error
-        auto read_batch = [&](size_t f0, size_t n, uint8_t* dst) -> std::string {
-            std::vector<std::string> errs(nread);
-            auto work = [&](unsigned t) {
-                for (size_t k = t; k < n && errs[t].empty(); k += nread) {
-                    const std::string& path = v.files[f0 + k];
-                    const int fd = open(path.c_str(), O_RDONLY);
-                    if (fd < 0) { errs[t] = "cannot open " + path; return; }
-                    b200::ImageInfo fi = v.info;
-                    if (f0 + k > 0) {
-                        std::vector<uint8_t> head(65536);
-                        const ssize_t hn = pread(fd, head.data(), head.size(), 0);
-                        std::string err;
-                        const bool ok = v.kind == 'd' ? b200::parse_dpx(head.data(), hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &err)
-                                                      : b200::parse_tiff(head.data(), hn > 0 ? (size_t)hn : 0, file_size(path), &fi, &err);
-                        if (!ok || fi.width != v.info.width || fi.height != v.info.height || fi.layout != v.info.layout) {
-                            close(fd);
-                            errs[t] = path + ": " + (ok ? std::string("geometry differs from the first frame") : err);
-                            return;
-                        }
-                    }
-                    if (!read_at(fd, dst + k * fb, fb, fi.data_offset)) { close(fd); errs[t] = "cannot read " + path; return; }
-                    close(fd);
-                }
-            };
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < nread; t++) th.emplace_back(work, t);
-            work(0);
-            for (auto& x : th) x.join();
-            for (auto& e : errs) if (!e.empty()) return e;
-            return "";
-        };
-        std::vector<const uint8_t*> ptrs(B);
-        std::vector<size_t> off(B), len(B);
-        pc.mark("pinned buffers");
-        std::string rerr = read_batch(0, std::min(B, v.files.size()), h_in[0]);
-        pc.mark("first batch read");
-        if (!rerr.empty()) { cleanup(); return fail(rerr, B200_ERR_IO); }
-        int cur = 0;
-        for (size_t f0 = 0; f0 < v.files.size(); f0 += B) {
-            const size_t n = std::min(B, v.files.size() - f0);
-            std::string next_err;
-            std::thread prefetch;
-            if (pin1.joinable()) { pin1.join(); if (!in1_ok) { cleanup(); return fail("cannot allocate pinned host buffers"); } }
-            if (f0 + B < v.files.size())
-                prefetch = std::thread([&, f0] { next_err = read_batch(f0 + B, std::min(B, v.files.size() - f0 - B), h_in[cur ^ 1]); });
-            for (size_t k = 0; k < n; k++) ptrs[k] = h_in[cur] + k * fb;
-            int rc = b200_ffv1_submit_host(E, ptrs.data(), (int32_t)n);
-            const void* d_arena = nullptr;
-            if (!rc) rc = b200_ffv1_packets_device(E, &d_arena, off.data(), len.data(), (int32_t)n);   // waits for the encode
-            pc.mark("encode (batch)");
-            bool mux_ok = rc == 0;
-            // packet k+1 crosses PCIe while packet k is written to the file
-            auto fetch = [&](size_t k) -> bool {
-                const int sl = (int)(k & 1);
-                if (len[k] > ring_cap) {                       // a packet larger than 1.25 x the frame: grow the ring
-                    cudaStreamSynchronize(cs);
-                    cudaFreeHost(h_ring[0]); cudaFreeHost(h_ring[1]);
-                    ring_cap = len[k] + (len[k] >> 3);
-                    if (cudaHostAlloc((void**)&h_ring[0], ring_cap, cudaHostAllocDefault) != cudaSuccess ||
-                        cudaHostAlloc((void**)&h_ring[1], ring_cap, cudaHostAllocDefault) != cudaSuccess) return false;
-                }
-                return cudaMemcpyAsync(h_ring[sl], static_cast<const uint8_t*>(d_arena) + off[k], len[k], cudaMemcpyDeviceToHost, cs) == cudaSuccess &&
-                       cudaEventRecord(cev[sl], cs) == cudaSuccess;
-            };
-            if (mux_ok) mux_ok = fetch(0);
-            for (size_t k = 0; k < n && mux_ok; k++) {
-                if (cudaEventSynchronize(cev[k & 1]) != cudaSuccess) { mux_ok = false; break; }
-                // the ring may only be re-used (or re-allocated) once the block that lives in it has been written
-                const int64_t t_ms = (int64_t)std::llround(1000.0 * (double)(f0 + k) / v.fps);
-                if (k + 1 < n && len[k + 1] <= ring_cap && !fetch(k + 1)) { mux_ok = false; break; }
-                mux_ok = flush_audio_until(t_ms) && mux.write_block(v.track, t_ms, h_ring[k & 1], len[k]);
-                if (mux_ok && k + 1 < n && len[k + 1] > ring_cap) mux_ok = fetch(k + 1);
-            }
-            pc.mark("mux write (batch)");
-            if (prefetch.joinable()) prefetch.join();
-            pc.mark("wait for next batch read");
-            if (rc) { cleanup(); return fail(std::string("ffv1 encode: ") + b200_last_error()); }
-            if (!mux_ok) { cleanup(); return fail(mux.error(), B200_ERR_IO); }
-            if (!next_err.empty()) { cleanup(); return fail(next_err, B200_ERR_IO); }
-            cur ^= 1;
-        }
-        cudaStreamSynchronize(cs);
-        cudaFreeHost(h_in[0]);
-        if (h_in[1]) cudaFreeHost(h_in[1]);
-        cudaFreeHost(h_ring[0]); cudaFreeHost(h_ring[1]);
-        cudaEventDestroy(cev[0]); cudaEventDestroy(cev[1]);
-        cudaStreamDestroy(cs);
+        std::string verr;
+        const int rc = encode_video_stream(videos[vi], encs[vi], devices, frames_in_flight, nthreads, slices, context, slicecrc, mux, flush_audio_until, pc, &verr);
+        encs[vi] = nullptr;                    // closed by the workers
+        if (rc) { cleanup(); return fail(verr, rc); }
     }
     if (!flush_audio_until(INT64_MAX) || !mux.close()) { cleanup(); return fail(mux.error(), B200_ERR_IO); }
     pc.mark("mux close");

@@ -11,6 +11,7 @@
 
 #include "ffv1_host.h"
 #include "ffv1_kernels.cuh"
+#include "sm_partition.h"
 
 namespace {
 
@@ -43,6 +44,12 @@ struct b200_ffv1_enc {
                                     // B = 128, but the optimum moves with B and with where the CTAs land: DESIGN.md §4)
     b200::EncArgs argsN[kPar];      // [0] unused (= args); [p] same as args with the band buffers of set p
     cudaStream_t sm = nullptr, sr = nullptr, se = nullptr;   // model / range / emit streams
+    // SM partition (green contexts): k_range on SMs of its own, k_model on the rest; k_emit either on a third part
+    // (emit_mode 0), behind k_model on the model stream (1, default) or behind k_range on the range stream (2)
+    b200::SmPartition part;
+    int emit_mode = 0;
+    bool scratch_dirty = true;                  // the slice scratch needs a full memset before the next encode
+    bool own_streams = true, own_se = false;    // sm/sr (and se) were made by cudaStreamCreate, not by the partition
     cudaStream_t sc = nullptr;                               // host-to-device copies of the host entry point
     std::vector<cudaEvent_t> ev_h2d;                         // [band] rows of the band have arrived
     cudaEvent_t ev_start = nullptr, ev_model[kPar] = {}, ev_range[kPar] = {}, ev_emit[kPar] = {};
@@ -246,6 +253,9 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
         int reserve = 0;
         if (const char* e = getenv("B200_MODEL_RESERVE")) reserve = atoi(e);
         A.model_ctas = nsm - reserve > 1 ? nsm - reserve : 1;
+        A.range_smem = 28 * 1024;
+        if (const char* e = getenv("B200_RANGE_SMEM_KB")) A.range_smem = atoi(e) * 1024;
+        if (A.range_smem > 48 * 1024) A.range_smem = 48 * 1024;
     }
 #undef ALLOC
     cudaMemcpy(d_geom, S.slices.data(), sizeof(b200::SliceGeom) * ns, cudaMemcpyHostToDevice);
@@ -264,9 +274,50 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     }
     // equal priorities: with prioritised streams the device preempts k_model's CTAs (227 KB of state each) whenever
     // k_range / k_emit become runnable, which costs more than it gains (measured: 28.5 ms per band against 21 ms)
-    cudaStreamCreateWithFlags(&E->sm, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&E->sr, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&E->se, cudaStreamNonBlocking);
+    {
+        // Partition: B200_RANGE_SMS SMs (default 24) to k_range, optionally B200_EMIT_SMS to k_emit, the rest to k_model.
+        // B200_NO_PARTITION=1 (or a driver without green contexts) falls back to three plain streams on the whole device.
+        int range_sms = 24, emit_sms = 0;
+        if (const char* e = getenv("B200_RANGE_SMS")) range_sms = atoi(e);
+        if (const char* e = getenv("B200_EMIT_SMS")) emit_sms = atoi(e);
+        E->emit_mode = emit_sms > 0 ? 0 : 1;
+        if (const char* e = getenv("B200_EMIT_MODE")) E->emit_mode = atoi(e);
+        if (emit_sms > 0 && E->emit_mode != 0) emit_sms = 0;
+        bool parted = false;
+        if (!getenv("B200_NO_PARTITION") && range_sms > 0) {
+            std::vector<int> want;
+            want.push_back(range_sms);
+            if (emit_sms > 0) want.push_back(emit_sms);
+            want.push_back(0);
+            if (E->part.create(cfg->device, want)) {
+                const int last = E->part.parts() - 1;
+                E->sr = E->part.stream(0);
+                E->se = emit_sms > 0 ? E->part.stream(1) : nullptr;
+                E->sm = E->part.stream(last);
+                parted = E->sr && E->sm && (emit_sms == 0 || E->se);
+                if (parted) {
+                    A.model_ctas = E->part.sm_count(last);
+                    A.range_smem = 120 * 1024;           // one k_range CTA per SM of its partition
+                    A.range_sms = E->part.sm_count(0);
+                    for (int pz = 1; pz < E->kpar; pz++) {
+                        E->argsN[pz].model_ctas = A.model_ctas; E->argsN[pz].range_smem = A.range_smem; E->argsN[pz].range_sms = A.range_sms;
+                    }
+                }
+            } else if (getenv("B200_VERBOSE")) {
+                fprintf(stderr, "b200enc: no SM partition (%s)\n", E->part.why().c_str());
+            }
+        }
+        if (!parted) {
+            E->sm = E->sr = E->se = nullptr;
+            cudaStreamCreateWithFlags(&E->sm, cudaStreamNonBlocking);
+            cudaStreamCreateWithFlags(&E->sr, cudaStreamNonBlocking);
+            if (E->emit_mode != 0 && !getenv("B200_EMIT_MODE")) E->emit_mode = 0;
+        }
+        E->own_streams = !parted;
+        if (E->emit_mode == 0 && !E->se) { cudaStreamCreateWithFlags(&E->se, cudaStreamNonBlocking); E->own_se = true; }
+        if (getenv("B200_VERBOSE"))
+            fprintf(stderr, "b200enc: %s, k_model grid %d, emit mode %d\n", parted ? "SM partition on" : "whole device", A.model_ctas, E->emit_mode);
+    }
     cudaStreamCreateWithFlags(&E->sc, cudaStreamNonBlocking);
     E->ev_h2d.resize(A.nbands);
     for (auto& ev : E->ev_h2d) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -316,7 +367,9 @@ void b200_ffv1_close(b200_ffv1_enc* E) {
     for (int pz = 0; pz < b200_ffv1_enc::kPar; pz++)
         for (cudaEvent_t ev : {E->ev_model[pz], E->ev_range[pz], E->ev_emit[pz]}) if (ev) cudaEventDestroy(ev);
     for (auto& ev : E->ev_h2d) if (ev) cudaEventDestroy(ev);
-    for (cudaStream_t st : {E->sm, E->sr, E->se, E->sc}) if (st) cudaStreamDestroy(st);
+    if (E->own_streams) for (cudaStream_t st : {E->sm, E->sr}) if (st) cudaStreamDestroy(st);
+    if (E->own_se && E->se) cudaStreamDestroy(E->se);
+    if (E->sc) cudaStreamDestroy(E->sc);
     delete E;
 }
 
@@ -374,7 +427,12 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
     }
     CU(cudaMemsetAsync(A[0].flags, 0, 256, s));
     CU(cudaMemsetAsync(A[0].work_ctr, 0, (size_t)A[0].nbands * 4, s));
-    CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)n_frames * A[0].nslices * A[0].slice_cap, s));   // k_emit accumulates into it
+    // k_emit accumulates into the slice scratch: it is zeroed once at open and k_pack re-zeroes what a call has used; only a
+    // call that ended in an overflow leaves it dirty
+    if (E->scratch_dirty) {
+        CU(cudaMemsetAsync(A[0].scratch, 0, (size_t)E->max_frames * A[0].nslices * A[0].slice_cap, s));
+        E->scratch_dirty = false;
+    }
     // Three kernels per band on three streams: model(b) -> range(b) -> emit(b); model(b) reuses the band buffers of
     // parity b&1 once emit(b-2) has drained them. `s` (the caller's stream) forks into and joins from the three.
     // timing mode (b200_ffv1_set_timing) and B200_SERIAL run everything on the caller's stream so that CUDA events can
@@ -392,13 +450,15 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
     }
     if (tr) CU(cudaEventRecord(E->trace[(size_t)A[0].nbands * 6], s));
     E->trace_pending = tr;
-    cudaStream_t sm = serial ? s : E->sm, sr = serial ? s : E->sr, se = serial ? s : E->se;
+    const int emode = serial ? 2 : E->emit_mode;     // serial: everything on the caller's stream, emit right behind range
+    cudaStream_t sm = serial ? s : E->sm, sr = serial ? s : E->sr;
+    cudaStream_t se = serial ? s : emode == 1 ? E->sm : emode == 2 ? E->sr : E->se;
     uint64_t launches = 0;
     if (!serial) {
         CU(cudaEventRecord(E->ev_start, s));
         CU(cudaStreamWaitEvent(sm, E->ev_start, 0));
         CU(cudaStreamWaitEvent(sr, E->ev_start, 0));
-        CU(cudaStreamWaitEvent(se, E->ev_start, 0));
+        if (emode == 0) CU(cudaStreamWaitEvent(se, E->ev_start, 0));
     }
     const int nb = A[0].nbands;
     std::vector<std::pair<int, int>> srows;                      // distinct (y0, h) of the slice grid's rows
@@ -407,6 +467,18 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
             if (srows.empty() || srows.back().first != g.y0) srows.push_back({g.y0, g.h});
         if (!serial) { CU(cudaEventRecord(E->ev_start, s)); CU(cudaStreamWaitEvent(E->sc, E->ev_start, 0)); }
     }
+    // emit(band): after range(band); frees the band buffers of its set for model(band + kpar)
+    auto do_emit = [&](int band) -> int {
+        const int p = band % E->kpar;
+        if (!serial && emode != 2) CU(cudaStreamWaitEvent(se, E->ev_range[p], 0));
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 4], se));
+        CU(b200::launch_emit(A[p], n_frames, se));
+        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 5], se));
+        if (tm) CU(cudaEventRecord(E->tev[band * 4 + 3], s));
+        if (!serial) CU(cudaEventRecord(E->ev_emit[p], se));
+        launches++;
+        return 0;
+    };
     for (int band = 0; band < nb; band++) {
         const int p = band % E->kpar;
         if (host_frames) {
@@ -423,7 +495,8 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
                 }
             if (!serial) { CU(cudaEventRecord(E->ev_h2d[band], sc)); CU(cudaStreamWaitEvent(sm, E->ev_h2d[band], 0)); }
         }
-        if (!serial && band >= E->kpar) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
+        // the band buffers of set p are free once emit(band - kpar) has drained them (emode 1: that emit is earlier in this stream)
+        if (!serial && emode != 1 && band >= E->kpar) CU(cudaStreamWaitEvent(sm, E->ev_emit[p], 0));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 0], s));
         if (tr) CU(cudaEventRecord(E->trace[band * 6 + 0], sm));
         CU(b200::launch_model(A[p], band, n_frames, sm));
@@ -434,16 +507,22 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
         CU(b200::launch_range(A[p], band, n_frames, sr));
         if (tr) CU(cudaEventRecord(E->trace[band * 6 + 3], sr));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 2], s));
-        if (!serial) { CU(cudaEventRecord(E->ev_range[p], sr)); CU(cudaStreamWaitEvent(se, E->ev_range[p], 0)); }
-        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 4], se));
-        CU(b200::launch_emit(A[p], n_frames, se));
-        if (tr) CU(cudaEventRecord(E->trace[band * 6 + 5], se));
-        if (tm) CU(cudaEventRecord(E->tev[band * 4 + 3], s));
-        if (!serial) CU(cudaEventRecord(E->ev_emit[p], se));
-        launches += 3;
+        if (!serial) CU(cudaEventRecord(E->ev_range[p], sr));
+        launches += 2;
+        // emode 1: k_emit shares the model stream; emit(band - kpar + 1) goes in behind model(band), just ahead of the
+        // model launch that needs its buffers, so that range(band - kpar + 1) has had a whole model launch to finish
+        if (emode == 1) {
+            const int eb = band - (E->kpar - 1);
+            if (eb >= 0) { int r = do_emit(eb); if (r) return r; }
+        } else {
+            int r = do_emit(band); if (r) return r;
+        }
     }
+    if (emode == 1)
+        for (int eb = nb - (E->kpar - 1) < 0 ? 0 : nb - (E->kpar - 1); eb < nb; eb++) { int r = do_emit(eb); if (r) return r; }
     if (!serial) {
-        CU(cudaEventRecord(E->ev_done_e, se));
+        if (emode == 0) { CU(cudaEventRecord(E->ev_done_e, se)); CU(cudaStreamWaitEvent(s, E->ev_done_e, 0)); }
+        CU(cudaEventRecord(E->ev_done_e, sr));
         CU(cudaStreamWaitEvent(s, E->ev_done_e, 0));
         CU(cudaEventRecord(E->ev_done_m, sm));
         CU(cudaStreamWaitEvent(s, E->ev_done_m, 0));
@@ -496,6 +575,7 @@ static int collect(b200_ffv1_enc* E, int32_t n_frames, size_t* out_off, size_t* 
         }
         E->trace_pending = false;
     }
+    if (R.h_flags[0] & 7u) E->scratch_dirty = true;
     if (R.h_flags[0] & 1u) return fail(B200_ERR_OVERFLOW, "slice scratch overflow");
     if (R.h_flags[0] & 2u) return fail(B200_ERR_OVERFLOW, "packet arena overflow");
     if (R.h_flags[0] & 4u) return fail(B200_ERR_OVERFLOW, "plane-row needs more column segments than reserved");
@@ -548,6 +628,16 @@ int b200_ffv1_fetch_packets(b200_ffv1_enc* E, uint8_t* out, size_t out_cap, size
     if (total > out_cap) return fail(B200_ERR_OVERFLOW, "output buffer too small");
     CU(cudaMemcpyAsync(out, E->rs[set].arena, (size_t)total, cudaMemcpyDeviceToHost, E->sf));
     CU(cudaStreamSynchronize(E->sf));
+    return 0;
+}
+
+int b200_ffv1_packet_sizes(b200_ffv1_enc* E, size_t* out_off, size_t* out_len, int32_t n_frames, size_t* total_bytes) {
+    if (!E) return fail(B200_ERR_INVALID, "null encoder");
+    CU(cudaSetDevice(E->cfg.device));
+    uint64_t total = 0;
+    int r = collect(E, n_frames, out_off, out_len, &total, false, nullptr);
+    if (r) return r;
+    if (total_bytes) *total_bytes = (size_t)total;
     return 0;
 }
 

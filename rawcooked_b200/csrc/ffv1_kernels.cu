@@ -785,7 +785,6 @@ __device__ __forceinline__ void range_step(uint32_t sp, uint32_t c, uint32_t& ra
 }
 
 constexpr int kCkptRecs = 64;
-constexpr int kRangeDepth = 4;          // 16-record groups in flight per lane
 
 // 0xFF when the most significant bit of byte `byte` of v is set, else 0 (prmt's sign-replication mode)
 template <int kByte>
@@ -811,9 +810,43 @@ __device__ __forceinline__ uint32_t ldg_stream_u16(const void* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(32) k_range(const __grid_constant__ EncArgs A, int band, int nframes) {
-    const int lane = threadIdx.x;
-    const int gid = blockIdx.x * 32 + lane;
+// ---- k_range: the records reach the coder lanes through shared memory, asynchronously.
+// Every plane-row segment is padded to whole 128-record blocks, so the 32 lanes of a warp (32 slices) cross block boundaries
+// in the same iteration although their streams differ. At a boundary every lane asks for the block it will need two blocks
+// later with nine 16-byte cp.async copies (128 q bytes + 16 bit-plane bytes, global -> shared without passing through
+// registers), and waits for the one it is about to read, which was asked for 256 records earlier. The recurrence itself then
+// only reads shared memory: one 16-byte and one 2-byte load per 16 records, no global-memory latency in the chain, and the
+// cursor over the row segments runs once per 128 records instead of once per 16.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16v(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+
+constexpr int kRangeWarps = 4;                       // one per scheduler
+constexpr int kRangeSlots = 4;                       // blocks in a lane's ring: one being read, two on their way, one just read
+constexpr uint32_t kRangeSlotStride = 144 + 16;      // 128 q bytes + 16 bit-plane bytes (+ pad: spreads the lanes over the banks)
+constexpr uint32_t kRangeWarpBytes = kRangeSlots * 32 * kRangeSlotStride;
+// the rings take 80 KB; the CTA asks for more than half an SM's shared memory so that it has the SM to itself: a warp that
+// shares its scheduler with others of its kind slows down by the round-robin factor
+constexpr size_t kRangeSmem = 120 * 1024;
+static_assert(kRangeWarps * kRangeWarpBytes <= kRangeSmem, "k_range rings");
+
+__global__ void __launch_bounds__(32 * kRangeWarps) k_range(const __grid_constant__ EncArgs A, int band, int nframes) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = (blockIdx.x * kRangeWarps + warp) * 32 + lane;
     const bool in_range = gid < nframes * A.nslices;
     const int slice = in_range ? gid % A.nslices : 0;
     const SliceGeom g = A.geom[slice];
@@ -825,69 +858,94 @@ __global__ void __launch_bounds__(32) k_range(const __grid_constant__ EncArgs A,
     const size_t gsafe = in_range ? (size_t)gid : 0;
     const uint32_t* rc = A.rowcnt + gsafe * A.band_rows * 3 * nseg;
 
-    uint32_t total = 0;                                         // 16-record groups this lane consumes in this band
-    for (int t = 0; t < nt; t++) total += ((rc[t] + 127u) >> 7) << 3;
-    uint32_t maxg = total;
+    // 128-record blocks this lane consumes in this band, per stream (Y: plane 0, C: planes 1 and 2)
+    uint32_t totY = 0, totC = 0;
+    for (int t = 0; t < nt; t++) {
+        const uint32_t nbk = (rc[t] + 127u) >> 7;
+        if (((t / nseg) % 3) != 0) totC += nbk; else totY += nbk;
+    }
+    uint32_t maxb = totY + totC;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) maxg = max(maxg, __shfl_xor_sync(0xffffffffu, maxg, o));
+    for (int o = 16; o; o >>= 1) maxb = max(maxb, __shfl_xor_sync(0xffffffffu, maxb, o));
 
     uint32_t range = 0xFF00u, cnt = 0;
     if (valid && band > 0) { const CoderState s = A.cstate[gid]; range = s.range; cnt = s.pos; }
 
-    const uint8_t* qY = A.qY + gsafe * A.capY;
-    const uint8_t* qC = A.qC + gsafe * A.capC;
-    const uint8_t* bY = A.bY + gsafe * (A.capY >> 3);
-    const uint8_t* bC = A.bC + gsafe * (A.capC >> 3);
+    const uint8_t* gqY = A.qY + gsafe * A.capY;
+    const uint8_t* gqC = A.qC + gsafe * A.capC;
+    const uint8_t* gbY = A.bY + gsafe * (A.capY >> 3);
+    const uint8_t* gbC = A.bC + gsafe * (A.capC >> 3);
     uint2* kY = A.ckptY + gsafe * (A.capY / kCkptRecs);
     uint2* kC = A.ckptC + gsafe * (A.capC / kCkptRecs);
 
-    // cursor over the lane's segments
+    // this lane's ring: slot k at ring + k * 32 * kRangeSlotStride
+    const uint32_t ring = smem_addr(smem_raw) + (uint32_t)warp * kRangeWarpBytes + (uint32_t)lane * kRangeSlotStride;
+    auto slot_at = [&](uint32_t k) { return ring + k * 32u * kRangeSlotStride; };
+
+    // block cursor (fetch side): the lane's blocks in bitstream order
     int t = -1;
-    uint32_t rem = 0, giY = 0, giC = 0, isC = 0;
+    uint32_t rem = 0, bkY = 0, bkC = 0, isC = 0;
     uint32_t cnt_pref = nt > 0 ? rc[0] : 0u;
-    uint4 Q[kRangeDepth];
-    uint32_t Bw[kRangeDepth], M[kRangeDepth];                   // bits of the group; M: bit 31 checkpoint due, bit 30 C stream, low bits group index
-    auto load_next = [&](int u) {
+    // asks for the lane's next block into slot k; returns its tag: bit 31 = a block, bit 30 = C stream, low bits = block index
+    auto fetch_block = [&](uint32_t k) -> uint32_t {
         while (rem == 0 && t + 1 < nt) {
             t++;
             const uint32_t c = cnt_pref;
             cnt_pref = t + 1 < nt ? rc[t + 1] : 0u;
-            rem = ((c + 127u) >> 7) << 3;
+            rem = (c + 127u) >> 7;
             isC = ((t / nseg) % 3) != 0;
         }
-        if (rem == 0) {
-            Q[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            Bw[u] = 0; M[u] = 0;
-            return;
+        uint32_t tag = 0;
+        if (rem) {
+            rem--;
+            const uint32_t bi = isC ? bkC : bkY;
+            const uint8_t* q = (isC ? gqC : gqY) + (size_t)bi * 128u;
+            const uint8_t* b = (isC ? gbC : gbY) + (size_t)bi * 16u;
+            const uint32_t dst = slot_at(k);
+#pragma unroll
+            for (int i = 0; i < 8; i++) cp_async16(dst + i * 16, q + i * 16);
+            cp_async16(dst + 128, b);
+            if (isC) bkC = bi + 1; else bkY = bi + 1;
+            tag = 0x80000000u | (isC << 30) | bi;
         }
-        rem--;
-        const uint32_t gi = isC ? giC : giY;
-        Q[u] = ldg_stream16((isC ? qC : qY) + (size_t)gi * 16);
-        Bw[u] = ldg_stream_u16((isC ? bC : bY) + (size_t)gi * 2);
-        M[u] = gi | (isC << 30) | ((gi & 3u) == 0 ? 0x80000000u : 0u);
-        if (isC) giC++; else giY++;
+        cp_async_commit();                      // an empty group when the lane has run out of blocks: the counts stay in step
+        return tag;
     };
+    uint32_t tags[kRangeSlots];                 // tag of the block in each slot (compile-time indexed: the block loop is unrolled by 4)
+    tags[0] = fetch_block(0);
+    tags[1] = fetch_block(1);
+    tags[2] = tags[3] = 0;
+
+    for (uint32_t b0 = 0; b0 < maxb; b0 += kRangeSlots) {
 #pragma unroll
-    for (int u = 0; u < kRangeDepth; u++) load_next(u);
-    for (uint32_t gi0 = 0; gi0 < maxg; gi0 += kRangeDepth) {
+        for (int k = 0; k < kRangeSlots; k++) {
+            // block b0 + k lives in slot k; ask for block b0 + k + 2 (its slot held block b0 + k - 2: read long ago), then wait
+            // until at most the two newest requests are pending
+            tags[(k + 2) % kRangeSlots] = fetch_block((uint32_t)((k + 2) % kRangeSlots));
+            cp_async_wait<2>();
+            const uint32_t tag = tags[k];
+            const bool have = (tag & 0x80000000u) != 0;
+            const uint32_t sl = slot_at((uint32_t)k);
+            uint2* ck = ((tag >> 30) & 1u ? kC : kY) + (size_t)(tag & 0x3FFFFFFFu) * 2u;
 #pragma unroll
-        for (int u = 0; u < kRangeDepth; u++) {
-            const uint4 q = Q[u];
-            const uint32_t nbits = ~Bw[u];
-            const uint32_t m = M[u];
-            load_next(u);
-            if (m & 0x80000000u) {
-                uint2* ck = ((m >> 30) & 1u ? kC : kY) + ((m & 0x3FFFFFFFu) >> 2);
-                *ck = make_uint2(range, cnt);
-            }
-            const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
+            for (int gI = 0; gI < 8; gI++) {
+                uint4 q = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);      // no-op records for a lane without a block
+                uint32_t nbits = 0xFFFFFFFFu;
+                if (have) {
+                    q = lds_v4(sl + gI * 16);
+                    nbits = ~lds_u16v(sl + 128 + gI * 2);
+                    if ((gI & 3) == 0) ck[gI >> 2] = make_uint2(range, cnt);                   // checkpoint every 64 records
+                }
+                const uint32_t ww[4] = {q.x, q.y, q.z, q.w};
 #define RSTEP(k) range_step(get_byte<((k) & 3)>(ww[(k) >> 2]) + 1u, msb_mask<((k) >> 3)>(nbits << (7 - ((k) & 7))), range, cnt);   /* c = 255 when the bit is 0 */
-            RSTEP(0) RSTEP(1) RSTEP(2) RSTEP(3) RSTEP(4) RSTEP(5) RSTEP(6) RSTEP(7)
-            RSTEP(8) RSTEP(9) RSTEP(10) RSTEP(11) RSTEP(12) RSTEP(13) RSTEP(14) RSTEP(15)
+                RSTEP(0) RSTEP(1) RSTEP(2) RSTEP(3) RSTEP(4) RSTEP(5) RSTEP(6) RSTEP(7)
+                RSTEP(8) RSTEP(9) RSTEP(10) RSTEP(11) RSTEP(12) RSTEP(13) RSTEP(14) RSTEP(15)
 #undef RSTEP
+            }
         }
     }
-    if (in_range) { A.used[gsafe * 2] = giY >> 2; A.used[gsafe * 2 + 1] = giC >> 2; }
+    cp_async_wait<0>();
+    if (in_range) { A.used[gsafe * 2] = totY << 1; A.used[gsafe * 2 + 1] = totC << 1; }
     if (valid) {
         if (r1 == g.h) {
             range_step(127u, 255u, range, cnt);                    // terminator: state 129, bit 0 (FFV1_Slice.cpp:334-343)
@@ -906,16 +964,16 @@ __global__ void __launch_bounds__(32) k_range(const __grid_constant__ EncArgs A,
     }
 }
 
-// k_emit: grid (pieces of 256 x 64 records, stream Y/C, frame*slice)
+// k_emit: grid (frame*slice, stream Y/C, pieces of 256 x 64 records): the large dimension in x, which has no 65535 limit
 constexpr int kEmitThreads = 256;
 constexpr int kEmitWords = 22;          // local window: word 0 spare, then stream words (c0>>2)-1 ... (c0>>2)+19
 
 __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ EncArgs A) {
     __shared__ uint32_t s_loc[kEmitWords][kEmitThreads];
-    const int gid = blockIdx.z, stream = blockIdx.y, tid = threadIdx.x;
+    const int gid = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
     const uint32_t used = A.used[(size_t)gid * 2 + stream];
-    if (blockIdx.x * kEmitThreads >= used) return;
-    const uint32_t blk = blockIdx.x * kEmitThreads + tid;
+    if (blockIdx.z * kEmitThreads >= used) return;
+    const uint32_t blk = blockIdx.z * kEmitThreads + tid;
     if (blk >= used) return;
     const size_t cap = stream ? A.capC : A.capY;
     const uint4* src = reinterpret_cast<const uint4*>((stream ? A.qC : A.qY) + (size_t)gid * cap) + (size_t)blk * 4;
@@ -1085,6 +1143,15 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ E
     const uint32_t tail0 = head + (body << 4);
     if (tid < (int)(n - tail0)) dst[tail0 + tid] = src[(tail0 + tid) ^ 3];
     __syncthreads();
+    // zero on consume: k_emit accumulates into the slice stream with atomic adds, so the next encode call needs it zeroed.
+    // What this call touched ends a few words beyond byte n (k_emit's local window, k_range's flush): clearing it here costs
+    // a write of the bytes just read instead of a memset of the worst-case capacity before every call.
+    {
+        uint4* z = reinterpret_cast<uint4*>(A.scratch + (size_t)gid * A.slice_cap);
+        const uint32_t nz = (uint32_t)(min((size_t)n + 160, A.slice_cap) + 15) >> 4;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = tid; i < nz; i += kPackThreads) z[i] = zero;
+    }
     if (tid == 0) {
         uint8_t f[8] = {(uint8_t)(n >> 16), (uint8_t)(n >> 8), (uint8_t)n, 0, 0, 0, 0, 0};
         if (A.ec) {
@@ -1106,6 +1173,7 @@ cudaError_t configure_kernels(const EncArgs& a) {
     // every kernel asks for the same L1 / shared-memory split as k_model: an SM cannot hold CTAs of two kernels that want
     // different splits, and k_range / k_emit / k_pack must run beside k_model's CTAs, not after them
     cudaFuncSetAttribute(k_range, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRangeSmem);
     cudaFuncSetAttribute(k_emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_pack, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1122,24 +1190,18 @@ cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s
 }
 
 cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s) {
-    int n = nframes * a.nslices;
-    // k_range is one latency-critical warp per CTA: beside k_model's warps (or more than two of its own kind per scheduler) it
-    // slows down by the scheduler's round-robin factor. The (unused) dynamic shared memory keeps it at 8 CTAs per SM and off
-    // the SMs k_model occupies; its high-priority stream hands it the first SMs k_model's CTAs leave.
-    static int range_smem = 0;
-    if (!range_smem) {
-        range_smem = 28 * 1024;
-        if (const char* e = getenv("B200_RANGE_SMEM_KB")) range_smem = atoi(e) * 1024;
-        if (range_smem > 48 * 1024) cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize, range_smem);
-    }
-    k_range<<<(n + 31) / 32, 32, range_smem, s>>>(a, band, nframes);
+    const int n = nframes * a.nslices;
+    const int warps = (n + 31) / 32;
+    // one lane per (frame, slice); CTAs of four warps, one per scheduler. The record rings (168 KB) keep a CTA alone on its
+    // SM: a warp that shares its scheduler with others of its kind slows down by the round-robin factor.
+    k_range<<<(warps + kRangeWarps - 1) / kRangeWarps, 32 * kRangeWarps, kRangeSmem, s>>>(a, band, nframes);
     return cudaGetLastError();
 }
 
 cudaError_t launch_emit(const EncArgs& a, int nframes, cudaStream_t s) {
     int n = nframes * a.nslices;
     const unsigned nblk = (unsigned)((a.capC / kCkptRecs) + kEmitThreads - 1) / kEmitThreads;
-    k_emit<<<dim3(nblk, 2, n), kEmitThreads, 0, s>>>(a);
+    k_emit<<<dim3(n, 2, nblk), kEmitThreads, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -78,7 +78,10 @@ struct EncArgs {
     uint8_t* arena;
     size_t arena_cap;
     uint32_t* work_ctr;           // [nbands] next work item of k_model's persistent grid (zeroed per encode call)
-    int32_t model_ctas;           // CTAs of k_model's grid (SMs minus the ones left to k_range / k_emit)
+    int32_t model_ctas;           // CTAs of k_model's grid (the SMs of its partition, or SMs minus the ones left to k_range / k_emit)
+    int32_t range_smem;           // dynamic shared memory k_range asks for (unused by the kernel): keeps it off k_model's SMs
+                                  // when the device is not partitioned, keeps it at one CTA per SM inside a partition
+    int32_t range_sms;            // SMs of k_range's partition (0: the device is not partitioned)
     uint32_t* flags;              // [0] overflow flag, [2..3] total bins, [16..] phase cycles (-DB200_PHASE_TIMING)
 };
 

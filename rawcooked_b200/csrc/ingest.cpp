@@ -127,15 +127,37 @@ bool parse_wav(const uint8_t* h, size_t n, uint64_t file_size, WavInfo* out, std
     return false;
 }
 
+// ffmpeg's image2 patterns (libavformat/utils av_get_frame_filename): "%d", "%0Nd" and "%%" only, exactly one number. The
+// pattern comes from argv, so it is parsed by hand: it never reaches a printf-style function as the format.
+static bool image2_name(const std::string& pattern, long long n, std::string* out) {
+    out->clear();
+    bool have_number = false;
+    for (size_t i = 0; i < pattern.size(); i++) {
+        const char c = pattern[i];
+        if (c != '%') { out->push_back(c); continue; }
+        if (i + 1 < pattern.size() && pattern[i + 1] == '%') { out->push_back('%'); i++; continue; }
+        size_t j = i + 1;
+        int width = 0;
+        const bool zero = j < pattern.size() && pattern[j] == '0';
+        while (j < pattern.size() && pattern[j] >= '0' && pattern[j] <= '9') { width = width * 10 + (pattern[j] - '0'); if (width > 64) return false; j++; }
+        if (j >= pattern.size() || pattern[j] != 'd' || have_number) return false;     // any other conversion is refused
+        std::string digits = std::to_string(n < 0 ? -n : n);
+        if ((int)digits.size() < width) digits.insert(0, (size_t)width - digits.size(), zero ? '0' : ' ');
+        if (n < 0) digits.insert(0, "-");
+        *out += digits;
+        have_number = true;
+        i = j;
+    }
+    return have_number;
+}
+
 std::vector<std::string> expand_image2(const std::string& pattern, long long start) {
     std::vector<std::string> out;
-    const size_t pc = pattern.find('%');
-    if (pc == std::string::npos) { if (file_exists(pattern)) out.push_back(pattern); return out; }
-    char buf[4096];
+    if (pattern.find('%') == std::string::npos) { if (file_exists(pattern)) out.push_back(pattern); return out; }
+    std::string name;
     for (long long n = start;; n++) {
-        snprintf(buf, sizeof buf, pattern.c_str(), (int)n);
-        if (!file_exists(buf)) break;
-        out.push_back(buf);
+        if (!image2_name(pattern, n, &name) || !file_exists(name)) break;
+        out.push_back(name);
     }
     return out;
 }

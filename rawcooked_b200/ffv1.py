@@ -52,6 +52,7 @@ def load_library():
     L.b200_ffv1_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.b200_ffv1_packets_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32]
     L.b200_ffv1_fetch_packets.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32]
+    L.b200_ffv1_packet_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(C.c_size_t)]
     L.b200_ffv1_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.b200_ffv1_set_timing.argtypes = [C.c_void_p, C.c_int32]
     L.b200_ffv1_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]

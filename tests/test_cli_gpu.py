@@ -96,3 +96,95 @@ def test_rawcooked_tiff_plus_6ch_96k_wav(tmp_path):
     victim.write_bytes(bytes(b))
     code2, out2 = run_rawcooked(["--check", name + ".mkv", "-o", "./"], cwd=str(tmp_path))
     assert OK not in out2 and ("not same" in out2 or code2 != 0), out2
+
+
+def run_rawcooked_env(args, cwd, env):
+    rc = util.ref_rawcooked()
+    if rc is None:
+        pytest.skip("oracle/_ref/rawcooked not built")
+    p = subprocess.run([rc] + args, cwd=cwd, capture_output=True, text=True, timeout=600, stdin=subprocess.DEVNULL, env=dict(os.environ, **env))
+    return p.returncode, p.stdout + p.stderr
+
+
+def test_rawcooked_gaps_concat_lists(tmp_path):
+    # the reference's gaps.sh (Project/GNU/CLI/test/gaps.sh): numbering gaps make RAWcooked hand the encoder `-f concat`
+    # file lists instead of an image2 pattern, one list per image directory, three video tracks in one package
+    name = "gaps1"
+    layout, w, h = S.DPX_RGB_16_BE, 64, 48
+    numbers = {"image1": [0, 6], "image2": [0, 1], "image3": [0, 1, 5, 6]}
+    seed = 400
+    for sub, nums in numbers.items():
+        d = tmp_path / name / sub
+        os.makedirs(d)
+        for n in nums:
+            seed += 1
+            open(d / ("%06d.dpx" % n), "wb").write(S.dpx_file(w, h, layout, S.synth_payload(w, h, layout, seed, "grain"), n))
+    code, out = run_rawcooked(["--accept-gaps", "--check", "-b", B200ENC, name], cwd=str(tmp_path))
+    assert code == 0, out
+    assert OK in out, out
+    # without --accept-gaps and with -n the reference refuses before it launches the encoder
+    os.remove(tmp_path / (name + ".mkv"))
+    code2, out2 = run_rawcooked(["-n", "--check", "-b", B200ENC, name], cwd=str(tmp_path))
+    assert OK not in out2
+
+
+@pytest.mark.parametrize("env", [
+    {"B200_FRAMES_IN_FLIGHT": "2"},                                   # 7 frames: four batches through one worker
+    {"B200_FRAMES_IN_FLIGHT": "3", "B200_DEVICES": "0,0"},            # 10 frames: four batches over two workers (one GPU, two handles)
+    {"B200_FRAMES_IN_FLIGHT": "2", "B200_DEVICES": "0,0,0"},
+], ids=["one_worker", "two_workers", "three_workers"])
+def test_rawcooked_batches_and_workers(tmp_path, env):
+    # the front-end's pipeline: batches in flight, one worker per device entry, packets muxed in frame order
+    name = "multi"
+    n = 7 if "B200_DEVICES" not in env else 10
+    write_dpx_sequence(str(tmp_path / name), n, 320, 240, S.DPX_RGB_16_BE, 2000)
+    code, out = run_rawcooked_env(["--check", "-y", "-b", B200ENC, "-slices", "24", name], str(tmp_path), env)
+    assert code == 0, out
+    assert OK in out, out
+    victim = tmp_path / name / ("f_%06d.dpx" % (n - 1))
+    b = bytearray(victim.read_bytes())
+    b[5000] ^= 0x04
+    victim.write_bytes(bytes(b))
+    code2, out2 = run_rawcooked(["--check", name + ".mkv", "-o", "./"], cwd=str(tmp_path))
+    assert OK not in out2 and ("not same" in out2 or code2 != 0), out2
+
+
+def test_rawcooked_all_gpus(tmp_path):
+    # every visible GPU gets a worker (the default); with one GPU this is the single-worker path again
+    import torch
+    name = "allgpus"
+    n = 4 * max(1, torch.cuda.device_count()) + 1
+    write_dpx_sequence(str(tmp_path / name), n, 256, 192, S.DPX_RGB_10_FA_BE, 3000)
+    code, out = run_rawcooked_env(["--check", "-y", "-b", B200ENC, name], str(tmp_path), {"B200_FRAMES_IN_FLIGHT": "2"})
+    assert code == 0, out
+    assert OK in out, out
+
+
+def test_odd_width_16bit_dpx_through_reference(tmp_path):
+    # 16-bit DPX with an odd width: the file's lines carry 2 bytes of padding (the only layout the reference's parser sizes the
+    # file by, DPX.cpp:478-482). Whatever the reference's own check makes of such a file, the encoder must read the pixels
+    # from the padded rows: the packet it writes equals the oracle's for the padded payload.
+    name = "odd"
+    w, h, layout = 133, 66, S.DPX_RGB_16_BE
+    write_dpx_sequence(str(tmp_path / name), 2, w, h, layout, 4000)
+    code, out = run_rawcooked(["-y", "--no-check", "-b", B200ENC, name], cwd=str(tmp_path))
+    mkv = tmp_path / (name + ".mkv")
+    if not mkv.exists():
+        pytest.skip("the reference did not launch the encoder for this input: " + out[-300:])
+    data = mkv.read_bytes()
+    nh, nv = ffv1_grid(w, h, data)
+    want = util.oracle_encode(S.synth_payload(w, h, layout, 4000, "grain"), w, h, layout, nh, nv)
+    assert want in data
+
+
+def ffv1_grid(w, h, mkv_bytes):
+    # slice grid of the stream from the `-slices` value the reference chose: try the grids ffmpeg's search can produce
+    from rawcooked_b200 import ffv1
+    for slices in (4, 6, 9, 12, 16, 20, 24, 25, 30, 36, 42, 49, 56, 64):
+        try:
+            rec = ffv1.config_record(w, h, S.DPX_RGB_16_BE, slices=slices)
+        except Exception:      # noqa: BLE001
+            continue
+        if rec in mkv_bytes:
+            return ffv1.slice_grid(w, h, slices)
+    raise AssertionError("no known ConfigurationRecord in the MKV")

@@ -123,6 +123,8 @@ def test_config5_frame_8k_12bit():
         f = S.synth_payload(w, h, layout, 5000)
         p = enc.encode([f])[0]
         assert p == util.oracle_encode(f, w, h, layout, 8, 8)
+        if util.ref_available():
+            assert util.ref_decode(enc.config_record, p, w, h, layout, threads=8) == f.tobytes()
     finally:
         enc.close()
 
@@ -171,3 +173,96 @@ def test_device_resident_entry_point():
         assert st["launches"] > 0 and st["bins"] > 0
     finally:
         enc.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# more (frame, slice, plane-set) items than k_model has CTAs: the persistent grid's work loop, all three kernel variants
+# (k_model: > 8 bit with the bank-replicated one_state table; k_model_compact: 8 bit, 28-byte state rows; the lean variant is
+# what wide slices fall back to) and every way the pipeline can be scheduled (SM partition on/off, where k_emit runs,
+# three band-buffer sets)
+MANY = [
+    (S.DPX_RGB_16_BE, 320, 240, 24, 16),     # 16 x 24 x 2 = 768 items
+    (S.DPX_RGB_10_FA_BE, 320, 240, 24, 16),
+    (S.DPX_RGB_8, 320, 240, 24, 16),         # k_model_compact
+    (S.DPX_RGB_12_PACKED_BE, 328, 120, 12, 20),
+]
+
+
+def _many(layout, w, h, slices, n, env=None):
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        enc = ffv1.FFV1Encoder(w, h, layout, slices=slices, max_frames=n)
+        try:
+            nh, nv = enc.grid
+            assert n * nh * nv * 2 > 148 * 2
+            kinds = ("grain", "flat", "grain", "white", "const")
+            frames = [S.synth_payload(w, h, layout, 7000 + k, kinds[k % len(kinds)]) for k in range(n)]
+            pkts = enc.encode(frames)
+            for k, (f, p) in enumerate(zip(frames, pkts)):
+                assert p == util.oracle_encode(f, w, h, layout, nh, nv), "frame %d differs from the oracle" % k
+            # second call on the same handle (scratch re-use), fewer frames
+            again = enc.encode(frames[5:9])
+            assert again == pkts[5:9]
+            if util.ref_available():
+                assert util.ref_decode(enc.config_record, pkts[-1], w, h, layout) == frames[-1].tobytes()
+        finally:
+            enc.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("layout,w,h,slices,n", MANY)
+def test_more_items_than_ctas(layout, w, h, slices, n):
+    _many(layout, w, h, slices, n)
+
+
+@pytest.mark.parametrize("env", [
+    {"B200_NO_PARTITION": "1"},
+    {"B200_NO_PARTITION": "1", "B200_KPAR": "3", "B200_MODEL_RESERVE": "36"},
+    {"B200_RANGE_SMS": "8"},
+    {"B200_RANGE_SMS": "24", "B200_KPAR": "3"},
+    {"B200_RANGE_SMS": "16", "B200_EMIT_SMS": "16"},
+    {"B200_RANGE_SMS": "32", "B200_EMIT_MODE": "2"},
+], ids=lambda e: ",".join("%s=%s" % (k[5:], v) for k, v in e.items()))
+def test_scheduling_variants_bit_exact(env):
+    _many(S.DPX_RGB_16_BE, 320, 240, 24, 16, env)
+    _many(S.DPX_RGB_8, 256, 120, 12, 14, env)
+
+
+def test_slicecrc0_matches_oracle_and_reference():
+    # -slicecrc 0: ec = 0 in the ConfigurationRecord, 3-byte slice tails (FFV1_Slice.cpp:247-253 reads the CRC only when ec)
+    w, h, layout, slices = 200, 150, S.DPX_RGB_16_BE, 6
+    enc = ffv1.FFV1Encoder(w, h, layout, slices=slices, slicecrc=0, max_frames=3)
+    try:
+        nh, nv = enc.grid
+        assert enc.config_record == util.oracle_record(w, h, layout, nh, nv, 1, 0)
+        frames = [S.synth_payload(w, h, layout, 60 + k) for k in range(3)]
+        for f, p in zip(frames, enc.encode(frames)):
+            assert p == util.oracle_encode(f, w, h, layout, nh, nv, 1, 0)
+            if util.ref_available():
+                assert util.ref_decode(enc.config_record, p, w, h, layout) == f.tobytes()
+    finally:
+        enc.close()
+
+
+def test_odd_width_dpx_rows():
+    # 8-bit and 16-bit DPX pad every line to 32 bits (DPX.cpp:478-482): odd widths shift every row by the padding
+    for layout, w, h in ((S.DPX_RGB_16_BE, 133, 66), (S.DPX_RGB_16_LE, 67, 45), (S.DPX_RGB_8, 65, 47), (S.DPX_RGB_8, 130, 61)):
+        enc = ffv1.FFV1Encoder(w, h, layout, slices=4, max_frames=2)
+        try:
+            nh, nv = enc.grid
+            assert enc.frame_bytes == S.frame_bytes(w, h, layout)
+            frames = [S.synth_payload(w, h, layout, 80 + k) for k in range(2)]
+            for f, p in zip(frames, enc.encode(frames)):
+                assert p == util.oracle_encode(f, w, h, layout, nh, nv)
+                if util.ref_available():
+                    assert util.ref_decode(enc.config_record, p, w, h, layout) == f.tobytes()
+        finally:
+            enc.close()
