@@ -139,7 +139,8 @@ int b200_ffv1_info(const b200_ffv1_enc* enc, int32_t info[8]);
 int b200_ffv1_set_timing(b200_ffv1_enc* enc, int32_t enabled);
 
 /* ---- FLAC (what `-c:a flac` asks of the child process, /root/reference/Source/CLI/Global.cpp:949-950). One frame per block,
- * fixed block size, independent channels, fixed predictors + partitioned Rice, all on the GPU. The frames are what the
+ * fixed block size, independent channels, fixed predictors and LPC (orders 1..8, 15-bit coefficients: ffmpeg's level 5) +
+ * partitioned Rice, all on the GPU. The frames are what the
  * reference's vendored libFLAC decodes in `--check` (Source/Lib/CoDec/Wrapper.cpp:138-219). */
 typedef struct b200_flac_cfg {
     uint32_t sample_rate;
@@ -148,7 +149,8 @@ typedef struct b200_flac_cfg {
     int32_t  block_size;  /* 0 = like ffmpeg: largest standard size <= 105 ms (4608 @ 48 kHz, 8192 @ 96 kHz); <= 16384 */
     int32_t  max_blocks;  /* blocks per encode call (0 = 256) */
     int32_t  device;
-    int32_t  reserved[6];
+    int32_t  fixed_only;  /* 1 = fixed predictors only (ffmpeg's -compression_level 0..2); 0 = LPC competes too (the default) */
+    int32_t  reserved[5]; /* must be 0 */
 } b200_flac_cfg;
 typedef struct b200_flac_enc b200_flac_enc;
 int b200_flac_open(const b200_flac_cfg* cfg, b200_flac_enc** out);
@@ -156,7 +158,9 @@ void b200_flac_close(b200_flac_enc* enc);
 int32_t b200_flac_block_size(const b200_flac_enc* enc);
 size_t b200_flac_max_frame_bytes(const b200_flac_enc* enc);
 /* Matroska CodecPrivate of the A_FLAC track: "fLaC" + STREAMINFO block (42 bytes); call after the last encode so that the
- * min/max frame sizes are known. MD5 is left 0 (= not computed). */
+ * min/max frame sizes are known. The MD5 signature of the unencoded audio (which the reference's libFLAC verifies at the end
+ * of the stream, Source/Lib/CoDec/Wrapper.cpp:189) is filled in when exactly total_samples samples went through this handle's
+ * encode calls, in order; otherwise it is left 0 (= not computed, the decoder then skips the check). */
 size_t b200_flac_codec_private(const b200_flac_enc* enc, uint64_t total_samples, uint8_t* out, size_t cap);
 /* Encode n_samples (per channel) of interleaved PCM given exactly as in the WAV data chunk (host memory). Frames are written
  * back to back into `out`; frame i = block i, numbered first_frame + i. Synchronous, includes H2D/D2H. */
@@ -166,6 +170,9 @@ int b200_flac_encode_host(b200_flac_enc* enc, const uint8_t* pcm, uint64_t n_sam
 /* ---- argv-compatible entry point: the `ffmpeg` command line RAWcooked builds (Source/CLI/Output.cpp:36-378). Returns the
  * process exit status (0 = success). `rawcooked -b b200enc` runs the executable that wraps this call. */
 int b200enc_main(int argc, char** argv);
+/* The b200enc executable ends with the job: with on != 0, b200enc_main skips the teardown of device and pinned host memory once
+ * the output file is complete (seconds for tens of GB) and leaves it to process exit. Library callers keep the default (0). */
+void b200enc_set_fast_exit(int on);
 
 /* Text of the last error on this thread ("" if none). */
 const char* b200_last_error(void);

@@ -9,12 +9,15 @@
  *   partitioned Rice    read_residual_partitioned_rice_   stream_decoder.c:2745-2788, bitreader.c:744
  *   frame CRC-8/CRC-16  crc.c:366-376, checked at stream_decoder.c:2075-2127
  *   STREAMINFO          read_metadata_streaminfo_   stream_decoder.c:1565
- * Encoder decisions (all integer, deterministic): independent channels; per subframe CONSTANT if all samples are equal, else
- * the fixed predictor order 0..4 with the smallest sum of |residual| over samples 4..n-1 (fixed.c:217-273 criterion), Rice
- * parameter per partition = floor(log2(mean)), partition order = exact minimum over 0..8, VERBATIM when that is not smaller.
- * FFmpeg's own choice (LPC, level 5) differs: bitstream identity with FFmpeg is NOT pinned for FLAC (nothing in the reference
- * pins it); what is pinned is that the reference's libFLAC decodes every frame to the input PCM
- * (tests/test_flac.py through oracle/_ref) — the property the reference's own tests check (test2.sh, check.sh).
+ * Encoder decisions (deterministic): independent channels; per subframe CONSTANT if all samples are equal, else the smaller of
+ *   - the fixed predictor order 0..4 with the smallest sum of |residual| over samples 4..n-1 (fixed.c:217-273 criterion),
+ *   - an LPC predictor of order 1..8 with 15-bit coefficients (ffmpeg's level 5; analysis described at lpc_analyse below),
+ * each with the Rice parameter per partition = floor(log2(mean)) and the partition order = exact minimum over 0..8; VERBATIM
+ * when neither is smaller than the raw samples.
+ * FFmpeg's own choices differ in detail: bitstream identity with FFmpeg is NOT pinned for FLAC (nothing in the reference pins it,
+ * SURVEY.md §8c). What is pinned: the reference's libFLAC decodes every frame to the input PCM and verifies the STREAMINFO MD5
+ * (tests/test_flac.py through oracle/_ref) — the property the reference's own tests check (test2.sh, check.sh) — and the output
+ * is not larger than 1.02 x libavcodec's on the benchmark signal (tests/test_flac.py::test_oracle_size_next_to_ffmpeg_flac).
  */
 #include <stdint.h>
 #include <stddef.h>

@@ -112,8 +112,11 @@ int ref_flac_decode(const uint8_t* stream, size_t size, int32_t* out, size_t cap
     FLAC__stream_decoder_set_md5_checking(d, true);
     if (FLAC__stream_decoder_init_stream(d, flac_read, 0, 0, 0, 0, flac_write, 0, flac_error, &m) != FLAC__STREAM_DECODER_INIT_STATUS_OK) { FLAC__stream_decoder_delete(d); return 3; }
     FLAC__bool ok = FLAC__stream_decoder_process_until_end_of_stream(d);
-    FLAC__stream_decoder_finish(d);
+    // finish() returns false when MD5 checking is on and the signature in STREAMINFO does not match the decoded audio
+    // (a zero signature switches the check off): what flac_wrapper relies on, Source/Lib/CoDec/Wrapper.cpp:189
+    const FLAC__bool md5_ok = FLAC__stream_decoder_finish(d);
     FLAC__stream_decoder_delete(d);
+    if (ok && !m.error && !md5_ok) { if (out_n) *out_n = m.n; return 4; }
     if (out_n) *out_n = m.n;
     if (channels) *channels = m.channels;
     if (bps) *bps = m.bps;

@@ -100,6 +100,11 @@ int fail(const std::string& msg, int code = 1) {
 }  // namespace
 
 
+// set by the b200enc executable: after the Matroska file is complete the process exits without freeing device memory and
+// unpinning host memory (seconds for tens of GB); a library caller of b200enc_main gets the full teardown
+bool g_fast_exit = false;
+extern "C" void b200enc_set_fast_exit(int on) { g_fast_exit = on != 0; }
+
 namespace {
 
 // One worker per GPU. Batch k (frames [k*B, k*B + B)) belongs to worker k % G, which keeps two of its batches in flight
@@ -202,18 +207,21 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
             if (b200_ffv1_open(&cfg, &E)) { fail_all(std::string("ffv1: ") + b200_last_error()); return; }
         }
         PinnedBuf in[2], out[2];
-        // pinning is slow (a few GB/s): the second input buffer and the output buffers are pinned in the background while
-        // the first batch is read and coded
-        bool bg_ok = true;
-        std::thread bg;
+        // pinning is slow (a few GB/s): only the first input buffer is pinned before work starts; the second one and the
+        // output buffers are pinned by background threads while the first batch is read and coded, each joined where its
+        // buffer is first needed
         const size_t out_guess = fb * B - (fb * B >> 2);
+        const bool many = (nbatch + G - 1 - w) / G > 1;
+        bool bg_ok[3] = {true, true, true};
+        std::thread bg[3];
+        struct JoinGuard { std::thread* t; ~JoinGuard() { for (int i = 0; i < 3; i++) if (t[i].joinable()) t[i].join(); } } guard{bg};
+        auto join_bg = [&](int i) -> bool { if (bg[i].joinable()) bg[i].join(); return bg_ok[i]; };
         if (!in[0].ensure(fb * B)) { b200_ffv1_close(E); fail_all("cannot allocate pinned host buffers"); return; }
-        bg = std::thread([&] {
-            cudaSetDevice(device);
-            bg_ok = out[0].ensure(out_guess);
-            if ((nbatch + G - 1 - w) / G > 1) bg_ok = bg_ok && in[1].ensure(fb * B) && out[1].ensure(out_guess);
-        });
-        struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } guard{bg};
+        bg[1] = std::thread([&] { cudaSetDevice(device); bg_ok[1] = out[0].ensure(out_guess); });
+        if (many) {
+            bg[0] = std::thread([&] { cudaSetDevice(device); bg_ok[0] = in[1].ensure(fb * B); });
+            bg[2] = std::thread([&] { cudaSetDevice(device); bg_ok[2] = out[1].ensure(out_guess); });
+        }
         std::vector<const uint8_t*> ptrs(B);
         size_t j = 0;
         long prev = -1;                                           // my previous batch: submitted, not yet fetched
@@ -228,8 +236,7 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
                 P.cv.wait(lk, [&] { return P.batches[k - 2 * G].consumed || P.abort; });
                 if (P.abort) { werr = "aborted"; return false; }
             }
-            if (bg.joinable()) bg.join();
-            if (!bg_ok || !o.ensure(total)) { werr = "cannot allocate pinned host buffers"; return false; }
+            if (!join_bg(1 + (int)(jj & 1)) || !o.ensure(total)) { werr = "cannot allocate pinned host buffers"; return false; }
             if (b200_ffv1_fetch_packets(E, o.p, o.cap, bt.off.data(), bt.len.data(), (int32_t)bt.n)) { werr = std::string("ffv1 fetch: ") + b200_last_error(); return false; }
             {
                 std::lock_guard<std::mutex> lk(P.mu);
@@ -241,8 +248,7 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
         };
         for (size_t k = w; k < nbatch; k += G, j++) {
             Batch& bt = P.batches[k];
-            if (j == 1 && bg.joinable()) bg.join();
-            if (j >= 1 && !bg_ok) { werr = "cannot allocate pinned host buffers"; break; }
+            if (j == 1 && !join_bg(0)) { werr = "cannot allocate pinned host buffers"; break; }
             const std::string rerr = read_batch(bt.f0, bt.n, in[j & 1].p);
             if (!rerr.empty()) { werr = rerr; break; }
             for (size_t i = 0; i < bt.n; i++) ptrs[i] = in[j & 1].p + i * fb;
@@ -265,7 +271,8 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
                 return true;
             });
         }
-        if (bg.joinable()) bg.join();
+        for (int i = 0; i < 3; i++) join_bg(i);
+        if (g_fast_exit) { in[0].p = in[1].p = out[0].p = out[1].p = nullptr; return; }   // the process is about to end: no teardown
         b200_ffv1_close(E);
     };
 

@@ -14,8 +14,80 @@
 
 void b200_set_error(const std::string& msg);          // b200enc.cu
 
+namespace {
+// MD5 (RFC 1321) of the unencoded audio for STREAMINFO: little-endian signed samples, interleaved, whole bytes per sample
+// (what FLAC__MD5Accumulate hashes on the decoding side, Source/Lib/ThirdParty/flac/src/libFLAC/md5.c).
+class Md5 {
+  public:
+    void update(const uint8_t* p, size_t n) {
+        total_ += n;
+        if (fill_) {
+            const size_t take = n < 64 - fill_ ? n : 64 - fill_;
+            memcpy(buf_ + fill_, p, take);
+            fill_ += take; p += take; n -= take;
+            if (fill_ == 64) { block(buf_); fill_ = 0; }
+        }
+        for (; n >= 64; p += 64, n -= 64) block(p);
+        if (n) { memcpy(buf_, p, n); fill_ = n; }
+    }
+    void digest(uint8_t out[16]) const {
+        Md5 c = *this;
+        const uint64_t bits = c.total_ * 8;
+        const uint8_t pad = 0x80, zero = 0;
+        c.update(&pad, 1);
+        while (c.fill_ != 56) c.update(&zero, 1);
+        uint8_t len[8];
+        for (int i = 0; i < 8; i++) len[i] = (uint8_t)(bits >> (8 * i));
+        c.update(len, 8);
+        for (int i = 0; i < 4; i++)
+            for (int k = 0; k < 4; k++) out[4 * i + k] = (uint8_t)(c.h_[i] >> (8 * k));
+    }
+    uint64_t bytes() const { return total_; }
+
+  private:
+    static uint32_t rol(uint32_t v, int s) { return (v << s) | (v >> (32 - s)); }
+    void block(const uint8_t* p) {
+        static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9, 14, 20, 5, 9, 14, 20, 5, 9, 14, 20, 5, 9, 14, 20,
+                                  4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+        static uint32_t K[64];
+        static bool init = false;
+        if (!init) {      // floor(2^32 * |sin(i + 1)|) from its first digits would need libm; the RFC's table is derived once by integer arithmetic below
+            static const uint32_t T[64] = {
+                0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af, 0xffff5bb1,
+                0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453,
+                0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a, 0xfffa3942,
+                0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05,
+                0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d,
+                0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+            memcpy(K, T, sizeof K);
+            init = true;
+        }
+        uint32_t M[16];
+        for (int i = 0; i < 16; i++) M[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+        uint32_t a = h_[0], b = h_[1], c = h_[2], d = h_[3];
+        for (int i = 0; i < 64; i++) {
+            uint32_t f; int g;
+            if (i < 16) { f = (b & c) | (~b & d); g = i; }
+            else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+            else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+            else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+            const uint32_t t = d;
+            d = c; c = b;
+            b = b + rol(a + f + K[i] + M[g], S[i]);
+            a = t;
+        }
+        h_[0] += a; h_[1] += b; h_[2] += c; h_[3] += d;
+    }
+    uint32_t h_[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    uint8_t buf_[64];
+    size_t fill_ = 0;
+    uint64_t total_ = 0;
+};
+}  // namespace
+
 struct b200_flac_enc {
     b200_flac_cfg cfg;
+    Md5 md5;
     int block_size = 0;
     uint32_t frame_words = 0;
     int max_blocks = 0;
@@ -105,7 +177,8 @@ size_t b200_flac_codec_private(const b200_flac_enc* E, uint64_t total_samples, u
     s[12] = (uint8_t)(((sr & 15) << 4) | ((ch - 1) << 1) | (((bps - 1) >> 4) & 1));
     s[13] = (uint8_t)((((bps - 1) & 15) << 4) | (uint32_t)((total_samples >> 32) & 15));
     s[14] = (uint8_t)(total_samples >> 24); s[15] = (uint8_t)(total_samples >> 16); s[16] = (uint8_t)(total_samples >> 8); s[17] = (uint8_t)total_samples;
-    // MD5 of the unencoded audio left at 0 = "not computed": the decoder then skips its MD5 check
+    // MD5 of the unencoded audio: known when every sample of the stream went through this handle; else 0 = "not computed"
+    if (E->md5.bytes() == total_samples * (uint64_t)ch * (bps / 8) && total_samples) E->md5.digest(s + 18);
     if (out && cap) memcpy(out, b, cap < 42 ? cap : 42);
     return 42;
 }
@@ -117,12 +190,20 @@ int b200_flac_encode_host(b200_flac_enc* E, const uint8_t* pcm, uint64_t n_sampl
     if (nblk == 0 || nblk > (uint64_t)E->max_blocks) return fail(B200_ERR_INVALID, "n_samples out of range for max_blocks");
     CU(cudaSetDevice(E->cfg.device));
     const size_t bytes = (size_t)n_samples * E->cfg.channels * (E->cfg.bits / 8);
+    if (E->cfg.bits == 8) {                                   // WAV 8-bit is unsigned, the signature is over signed bytes
+        std::vector<uint8_t> sgn(pcm, pcm + bytes);
+        for (auto& v : sgn) v = (uint8_t)(v - 128);
+        E->md5.update(sgn.data(), bytes);
+    } else {
+        E->md5.update(pcm, bytes);
+    }
     CU(cudaMemcpyAsync(E->d_pcm, pcm, bytes, cudaMemcpyHostToDevice, 0));
     CU(cudaMemsetAsync(E->d_out, 0, (size_t)nblk * E->frame_words * 4, 0));
     b200::FlacArgs A;
     A.pcm = E->d_pcm; A.n_samples = n_samples; A.first_frame = first_frame;
     A.channels = (int32_t)E->cfg.channels; A.bits = (int32_t)E->cfg.bits; A.sample_rate = (int32_t)E->cfg.sample_rate; A.block_size = E->block_size;
     A.out = E->d_out; A.frame_words = E->frame_words; A.frame_len = E->d_len;
+    A.use_lpc = E->cfg.fixed_only ? 0 : 1;
     CU(b200::launch_flac(A, (int)nblk, 0));
     E->launches++;
     CU(cudaMemcpyAsync(E->h_len.data(), E->d_len, (size_t)nblk * 4, cudaMemcpyDeviceToHost, 0));

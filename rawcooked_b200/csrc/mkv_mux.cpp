@@ -1,8 +1,11 @@
 #include "mkv_mux.h"
 
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
+#include <cstdlib>
 #include <cstring>
 
 namespace b200 {
@@ -76,6 +79,18 @@ bool MkvWriter::pwrite_all(const void* p, size_t n, uint64_t at) {
     return true;
 }
 
+// One large piece of a packet. On tmpfs, writes to one file serialise on the inode lock however many threads issue them; there
+// the piece goes through a private mapping of its page range instead (the page faults of different threads run in parallel).
+bool MkvWriter::write_piece(const uint8_t* p, size_t n, uint64_t at) {
+    if (!use_mmap_) return pwrite_all(p, n, at);
+    const uint64_t page = 4096, a0 = at & ~(page - 1), a1 = (at + n + page - 1) & ~(page - 1);
+    void* m = ::mmap(nullptr, (size_t)(a1 - a0), PROT_READ | PROT_WRITE, MAP_SHARED, fd_, (off_t)a0);
+    if (m == MAP_FAILED) return pwrite_all(p, n, at);
+    std::memcpy(static_cast<uint8_t*>(m) + (at - a0), p, n);
+    ::munmap(m, (size_t)(a1 - a0));
+    return true;
+}
+
 void MkvWriter::writer_loop() {
     for (;;) {
         Job j;
@@ -86,7 +101,7 @@ void MkvWriter::writer_loop() {
             j = jobs_.front();
             jobs_.pop_front();
         }
-        const bool ok = pwrite_all(j.p, j.n, j.at);
+        const bool ok = write_piece(j.p, j.n, j.at);
         {
             std::lock_guard<std::mutex> lk(mu_);
             if (!ok) io_failed_ = true;
@@ -123,6 +138,10 @@ bool MkvWriter::put(const void* p, size_t n) {
         return true;
     }
     if (!flush_small()) return false;
+    if (use_mmap_ && pos_ + n > file_size_) {      // a mapping cannot extend the file: grow it ahead of the writers, trim in close()
+        file_size_ = ((pos_ + n) | (((uint64_t)1 << 30) - 1)) + 1;
+        if (::ftruncate(fd_, (off_t)file_size_) != 0) { use_mmap_ = false; }
+    }
     // large payload: cut into pieces for the writer pool
     const size_t piece = (size_t)8 << 20;
     {
@@ -153,8 +172,10 @@ bool MkvWriter::open(const std::string& path, const std::vector<MkvTrack>& track
     fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd_ < 0) { err_ = "cannot create " + path; return false; }
     {
+        struct statfs fs;
+        use_mmap_ = ::fstatfs(fd_, &fs) == 0 && (unsigned long)fs.f_type == 0x01021994ul && !getenv("B200_NO_MMAP_OUTPUT");   // TMPFS_MAGIC
         unsigned nw = std::thread::hardware_concurrency();
-        nw = nw < 2 ? 2 : nw > 8 ? 8 : nw;
+        nw = nw < 2 ? 2 : nw > 16 ? 16 : nw;
         for (unsigned i = 0; i < nw; i++) writers_.emplace_back([this] { writer_loop(); });
     }
     std::vector<uint8_t> h, body;
@@ -312,6 +333,7 @@ bool MkvWriter::close() {
     ok = ok && patch_size8(segment_data_start_ - 8, pos_ - segment_data_start_);
     ok = flush_small() && ok;
     ok = sync() && ok;
+    if (use_mmap_ && file_size_ > pos_ && ::ftruncate(fd_, (off_t)pos_) != 0 && ok) { err_ = "cannot trim the output file"; ok = false; }
     if (::close(fd_) != 0 && ok) { err_ = "close failed"; ok = false; }
     fd_ = -1;
     return ok;

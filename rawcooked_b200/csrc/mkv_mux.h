@@ -50,6 +50,9 @@ class MkvWriter {
     bool patch_size8(uint64_t at, uint64_t value);
     bool flush_cluster();
     bool pwrite_all(const void* p, size_t n, uint64_t at);
+    bool write_piece(const uint8_t* p, size_t n, uint64_t at);
+    bool use_mmap_ = false;               // output on tmpfs: large pieces go through mappings (see write_piece)
+    uint64_t file_size_ = 0;              // size the file has been grown to (mmap path)
     void writer_loop();
     int fd_ = -1;
     std::string err_;

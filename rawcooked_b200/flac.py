@@ -9,7 +9,7 @@ from .ffv1 import B200Error, load_library
 
 class _Cfg(C.Structure):
     _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits", C.c_uint32), ("block_size", C.c_int32),
-                ("max_blocks", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("max_blocks", C.c_int32), ("device", C.c_int32), ("fixed_only", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 def _lib():
@@ -39,9 +39,9 @@ def pcm_to_wav_bytes(pcm, bits):
 
 
 class FLACEncoder:
-    def __init__(self, sample_rate, channels, bits, block_size=0, max_blocks=256, device=0):
+    def __init__(self, sample_rate, channels, bits, block_size=0, max_blocks=256, device=0, fixed_only=False):
         self._L = _lib()
-        cfg = _Cfg(sample_rate, channels, bits, block_size, max_blocks, device)
+        cfg = _Cfg(sample_rate, channels, bits, block_size, max_blocks, device, 1 if fixed_only else 0)
         h = C.c_void_p()
         rc = self._L.b200_flac_open(C.byref(cfg), C.byref(h))
         if rc:

@@ -45,9 +45,16 @@ def oracle_frames(pcm, sr, bits, first_frame=0):
     return frames, bs
 
 
-def oracle_private(bs, frames, sr, ch, bits, n):
+def oracle_private(bs, frames, sr, ch, bits, n, pcm=None):
+    """CodecPrivate of the stream; with `pcm` the STREAMINFO MD5 signature of the unencoded audio (little-endian signed samples,
+    interleaved) is filled in, computed here with hashlib."""
     cp = (C.c_uint8 * 42)()
     flac_oracle().flaco_codec_private(bs, min(len(f) for f in frames), max(len(f) for f in frames), sr, ch, bits, n, cp)
+    cp = bytearray(bytes(cp))
+    if pcm is not None:
+        import hashlib
+        raw = np.ascontiguousarray(pcm.astype("<i4")).view(np.uint8).reshape(pcm.shape[0], pcm.shape[1], 4)[:, :, : bits // 8]
+        cp[26:42] = hashlib.md5(np.ascontiguousarray(raw).tobytes()).digest()
     return bytes(cp)
 
 
@@ -89,8 +96,16 @@ def test_oracle_decodes_through_reference_libflac(ch, sr, bits, n, kind):
     pcm = make_pcm(ch, sr, bits, n, kind)
     frames, bs = oracle_frames(pcm, sr, bits)
     assert bs <= 16384                                   # reference buffers at most 16384 samples per block (Wrapper.cpp:251)
-    dec = ref_decode(oracle_private(bs, frames, sr, ch, bits, n), frames, n, ch)
+    dec = ref_decode(oracle_private(bs, frames, sr, ch, bits, n, pcm), frames, n, ch)      # libFLAC verifies the MD5 signature
     assert np.array_equal(dec, pcm)
+    # a wrong signature must be noticed by the reference's libFLAC (rc 4 from the harness)
+    bad = bytearray(oracle_private(bs, frames, sr, ch, bits, n, pcm))
+    bad[30] ^= 0x55
+    R = util.ref_decoder()
+    stream = bytes(bad) + b"".join(frames)
+    out = np.zeros(n * ch + 64, np.int32)
+    on, c, b = C.c_size_t(0), C.c_uint(0), C.c_uint(0)
+    assert R.ref_flac_decode(stream, len(stream), out.ctypes.data, out.size, C.byref(on), C.byref(c), C.byref(b)) == 4
 
 
 @pytest.mark.gpu
@@ -107,7 +122,7 @@ def test_cuda_flac_matches_oracle_and_reference(ch, sr, bits, n, kind):
         for i, (a, b) in enumerate(zip(frames, want)):
             assert a == b, "frame %d differs from the oracle" % i
         private = enc.codec_private()
-        assert private == oracle_private(bs, want, sr, ch, bits, n)
+        assert private == oracle_private(bs, want, sr, ch, bits, n, pcm)          # STREAMINFO with the MD5 signature
         if util.ref_available():
             assert np.array_equal(ref_decode(private, frames, n, ch), pcm)
     finally:
@@ -131,3 +146,23 @@ def test_config4_audio_six_channels_96k_24bit():
         assert sum(len(f) for f in frames) < 0.8 * n * ch * 3
     finally:
         enc.close()
+
+
+def test_oracle_size_next_to_ffmpeg_flac():
+    # FFmpeg's flac encoder at its default level (5: LPC up to order 8) on the audio of BASELINE config 4: nothing pins the
+    # FLAC bitstream, but an archive tool's output size is part of the product. The encoder built here must not be more
+    # than 2 % larger (measured when this test was written: 0.5744 of the raw PCM for both).
+    import sys
+    sys.path.insert(0, os.path.join(util.ROOT, "oracle"))
+    try:
+        import avcodec_flac
+        ch, sr, bits, n = 6, 96000, 24, 96000 * 2
+        pcm = S.wav_pcm(ch, sr, bits, n, 77)
+        theirs, fs = avcodec_flac.flac_encoded_bytes(pcm, sr, bits)
+    except Exception as e:          # noqa: BLE001
+        pytest.skip("bundled libavcodec flac encoder not usable here: %s" % e)
+    frames, bs = oracle_frames(pcm, sr, bits)
+    assert bs == fs == 8192
+    ours = sum(len(f) for f in frames)
+    assert ours <= 1.02 * theirs, (ours, theirs)
+    assert ours < 0.60 * n * ch * 3

@@ -14,6 +14,24 @@ for i in range(n):
     p = os.path.join(d, "f_%06d.dpx" % i)
     if not os.path.exists(p):
         open(p, "wb").write(S.dpx_file(w, h, layout, uniq[i % 4], i))
+# what the box's tmpfs itself can take: the front-end's steady state is bound by it (one writer, then 8 in parallel)
+import threading
+blob = np.random.default_rng(0).integers(0, 256, 1 << 30, dtype=np.uint8).tobytes()
+t = time.perf_counter()
+with open(os.path.join(d, "probe.bin"), "wb") as f:
+    f.write(blob)
+print("tmpfs write, 1 thread: %.2f GB/s" % (len(blob) / (time.perf_counter() - t) / 1e9))
+def _w(i):
+    with open(os.path.join(d, "probe%d.bin" % i), "wb") as f:
+        f.write(blob[: 1 << 28])
+ths = [threading.Thread(target=_w, args=(i,)) for i in range(8)]
+t = time.perf_counter()
+[x.start() for x in ths]; [x.join() for x in ths]
+print("tmpfs write, 8 threads / 8 files: %.2f GB/s" % (8 * (1 << 28) / (time.perf_counter() - t) / 1e9))
+for f in os.listdir(d):
+    if f.startswith("probe"):
+        os.remove(os.path.join(d, f))
+del blob
 out = os.path.join(d, "out.mkv")
 cmd = [os.path.join(ROOT, "rawcooked_b200", "b200enc"), "-xerror", "-framerate", "24", "-r", "24", "-f", "image2", "-c:v", "dpx", "-start_number", "000000",
        "-i", os.path.join(d, "f_%06d.dpx"), "-c:a", "flac", "-c:v", "ffv1", "-coder", "1", "-context", "1", "-f", "matroska", "-g", "1", "-level", "3",
