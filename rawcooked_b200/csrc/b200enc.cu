@@ -163,6 +163,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
         if (fixed + reserve + 2 * (chunk_need + 256) > (size_t)dev_smem) continue;
         size_t capk = (((size_t)dev_smem - reserve - fixed) / 2) & ~(size_t)127;
         if (capk > row_need) capk = row_need;
+        if (capk > 32640) capk = 32640;             // record offsets inside the stage travel as 16-bit byte offsets (k_model chains, flat path)
         const int nsegk = capk >= row_need ? 1 : (int)(((size_t)wmax * maxbins + (capk - chunk_need) - 1) / (capk - chunk_need));
         if (capk > best_cap) { best = k; best_nseg = nsegk; best_cap = capk; }
         if (capk * 2 >= row_need) break;           // good enough: typical rows are far below the worst case

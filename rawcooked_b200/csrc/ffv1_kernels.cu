@@ -86,10 +86,10 @@ constexpr uint32_t kNopRec = 0x00FFu;
 //   qtab    5 x 256 int16    quantisation tables
 //   t1      one_state, indexed by q: either replicated per bank ([64][32] words: lane l reads word (q >> 2) * 32 + l, no
 //           bank conflicts whatever the 32 lanes look up) or a plain 256-byte table when shared memory is short
-//   val/ctx/off per sample of the plane-row being coded: folded residual (after the context-sign flip), context, first
-//           record of the sample relative to its 32-sample chunk
+//   ent     the samples of the plane-row being coded, grouped by context class (= owner warp), x order inside a class: folded
+//           residual (after the context-sign flip) | x << 18, context | first record of the sample in the stage << 16
 //   ctot    records per 32-sample chunk
-//   cmask   [chunk][class] which samples of the chunk belong to a context class (class = ctx mod 16 = owner warp)
+//   wcnt    [class][warp] samples of the class among the chunks that warp prepared in S1
 //   stage   the records of the plane-row (segment), 16 bit each, split into q bytes + bit-plane on the way out
 //
 // Per plane-row: S1 all samples in parallel: neighbours, context, residual, bin count, class masks -> S2 (K3) warp q
@@ -100,7 +100,7 @@ constexpr uint32_t kNopRec = 0x00FFu;
 // barrier inside S2.
 struct ModelSmem {
     uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b;
-    int32_t* val; uint16_t* ctx; uint16_t* off; uint32_t* ctot; uint32_t* cmask; uint32_t* misc; uint8_t* tpow; uint8_t* trans; uint16_t* stage;
+    uint2* ent; uint32_t* ctot; uint16_t* wcnt; uint32_t* misc; uint8_t* tpow; uint8_t* trans; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -111,11 +111,10 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int t1_rep)
     n += align16((size_t)3 * planes * wmax * 4);
     n += 5 * 256 * 2;
     n += rep ? 64 * 32 * 4 : 256;
-    n += align16((size_t)wmax * 4);          // val
-    n += align16((size_t)wmax * 2) * 2;      // ctx, off
+    n += align16((size_t)wmax * 8);          // ent
     const int nch = (wmax + 31) / 32;
     n += align16((size_t)nch * 4);           // ctot
-    n += (size_t)nch * kModelWarps * 4;      // cmask
+    n += align16((size_t)kModelWarps * kModelWarps * 2);      // wcnt
     n += kModelWarps * 64;                   // misc: per-lane landing place of the records of idle lanes
     n += 5 * 256;                            // tpow
     n += 512;                                // trans
@@ -132,12 +131,10 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     m.ring = reinterpret_cast<int32_t*>(base); base += align16((size_t)3 * planes * wmax * 4);
     m.qtab = reinterpret_cast<int16_t*>(base); base += 5 * 256 * 2;
     m.t1w = reinterpret_cast<uint32_t*>(base); m.t1b = base; base += rep ? 64 * 32 * 4 : 256;
-    m.val = reinterpret_cast<int32_t*>(base); base += align16((size_t)wmax * 4);
-    m.ctx = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
-    m.off = reinterpret_cast<uint16_t*>(base); base += align16((size_t)wmax * 2);
+    m.ent = reinterpret_cast<uint2*>(base); base += align16((size_t)wmax * 8);
     const int nch = (wmax + 31) / 32;
     m.ctot = reinterpret_cast<uint32_t*>(base); base += align16((size_t)nch * 4);
-    m.cmask = reinterpret_cast<uint32_t*>(base); base += (size_t)nch * kModelWarps * 4;
+    m.wcnt = reinterpret_cast<uint16_t*>(base); base += align16((size_t)kModelWarps * kModelWarps * 2);
     m.misc = reinterpret_cast<uint32_t*>(base); base += kModelWarps * 64;
     m.tpow = base; base += 5 * 256;
     m.trans = base; base += 512;
@@ -239,7 +236,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
         } else {
             for (int i = tid; i < 256; i += kModelThreads) S.t1b[i] = A.t1q[i];
         }
-        for (int i = tid; i < ((wmax + 31) / 32) * NW; i += kModelThreads) S.cmask[i] = 0;
         for (int i = tid; i < 5 * 256; i += kModelThreads) S.tpow[i] = A.tpow[i];
         // next state by (bit, state): the chains' only dependency from sample to sample is one look-up in this table
         for (int i = tid; i < 512; i += kModelThreads) {
@@ -320,41 +316,55 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
             const int32_t* cur = S.ring + ((size_t)((y + 3) % 3) * planes + pl) * wmax;
             const int32_t* prv = S.ring + ((size_t)((y + 2) % 3) * planes + pl) * wmax;
             const int32_t* pp2 = S.ring + ((size_t)((y + 1) % 3) * planes + pl) * wmax;
-            // ---- S1 (K2): prediction, context, fold, records per sample; class masks
-            for (int k = 0; k < KC; k++) {
-                const int c = k * NW + warp;
-                if (c >= nchunk) break;
-                const int x = c * 32 + lane;
-                const bool valid = x < w;
-                uint32_t nb = 0, cls = 32u + (uint32_t)lane;
-                if (valid) {
-                    const int T = prv[x];
-                    const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
-                    const int L = x > 0 ? cur[x - 1] : prv[0];                 // sample[0][-1] = sample[1][0]
-                    const int LT = x > 0 ? prv[x - 1] : pp2[0];                // what sample[1][-1] was set to one row earlier
-                    int ctx = S.qtab[(L - LT) & 255] + S.qtab[256 + ((LT - T) & 255)] + S.qtab[512 + ((T - RT) & 255)];
-                    if (A.is5) {
-                        const int LL = x > 1 ? cur[x - 2] : (x == 1 ? prv[0] : 0);
-                        const int TT = pp2[x];
-                        ctx += S.qtab[768 + ((LL - L) & 255)] + S.qtab[1024 + ((TT - T) & 255)];
-                    }
-                    int d = cur[x] - median3(L, L + T - LT, T);
-                    if (ctx < 0) { ctx = -ctx; d = -d; }
-                    d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
-                    S.val[x] = d;
-                    S.ctx[x] = (uint16_t)ctx;
-                    cls = ((uint32_t)ctx * 2654435761u) >> (32 - (NW == 16 ? 4 : 5));   // multiplicative hash: even class sizes
-                    nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
-                }
-                uint32_t incl = nb;
+            // ---- S1 (K2): prediction, context, fold, records per sample. Warp w prepares chunks [w KC, (w+1) KC) and keeps
+            // them in registers until the class lists can be laid out (after the barrier)
+            constexpr int KCMAX = (2048 / 32 + NW - 1) / NW;                       // wmax <= 2048
+            if (lane < NW) S.wcnt[lane * NW + warp] = 0;
+            __syncwarp();
+            int sv[KCMAX];
+            uint32_t scx[KCMAX], sof[KCMAX], spi[KCMAX];   // context | class << 16 (all ones: no sample), first record within the chunk, rank among my warp's samples of the class
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const uint32_t m = __match_any_sync(0xffffffffu, cls);
-                if (valid) {
-                    S.off[x] = (uint16_t)(incl - nb);
-                    if ((m & lt) == 0) S.cmask[c * NW + cls] = m;              // lowest lane of the class group
+            for (int k = 0; k < KCMAX; k++) {
+                const int c = warp * KC + k;
+                sv[k] = 0; scx[k] = 0xFFFFFFFFu; sof[k] = 0; spi[k] = 0;
+                if (k < KC && c < nchunk) {
+                    const int x = c * 32 + lane;
+                    const bool valid = x < w;
+                    uint32_t nb = 0, cls = 32u + (uint32_t)lane;
+                    int d = 0, ctx = 0;
+                    if (valid) {
+                        const int T = prv[x];
+                        const int RT = prv[x + 1 < w ? x + 1 : w - 1];            // sample[1][w] = sample[1][w-1]
+                        const int L = x > 0 ? cur[x - 1] : prv[0];                 // sample[0][-1] = sample[1][0]
+                        const int LT = x > 0 ? prv[x - 1] : pp2[0];                // what sample[1][-1] was set to one row earlier
+                        ctx = S.qtab[(L - LT) & 255] + S.qtab[256 + ((LT - T) & 255)] + S.qtab[512 + ((T - RT) & 255)];
+                        if (A.is5) {
+                            const int LL = x > 1 ? cur[x - 2] : (x == 1 ? prv[0] : 0);
+                            const int TT = pp2[x];
+                            ctx += S.qtab[768 + ((LL - L) & 255)] + S.qtab[1024 + ((TT - T) & 255)];
+                        }
+                        d = cur[x] - median3(L, L + T - LT, T);
+                        if (ctx < 0) { ctx = -ctx; d = -d; }
+                        d = (d << (32 - sbits)) >> (32 - sbits);                  // fold to sbits, sign-extended
+                        cls = NW == 16 ? ((uint32_t)ctx * 2654435761u) >> 28 : NW == 32 ? ((uint32_t)ctx * 2654435761u) >> 27
+                                                     : ((((uint32_t)ctx * 2654435761u) >> 16) * (uint32_t)NW) >> 16;   // multiplicative hash: even class sizes
+                        nb = d ? 2 * (31 - __clz(abs(d))) + 3 : 1;
+                    }
+                    uint32_t incl = nb;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    const uint32_t m = __match_any_sync(0xffffffffu, cls);
+                    const int leader = __ffs(m) - 1;
+                    uint32_t old = 0;
+                    if (valid && lane == leader) {                                  // my warp's running count of the class
+                        old = S.wcnt[cls * NW + warp];
+                        S.wcnt[cls * NW + warp] = (uint16_t)(old + (uint32_t)__popc(m));
+                    }
+                    old = __shfl_sync(0xffffffffu, old, leader);
+                    __syncwarp();
+                    if (valid) { sv[k] = d; scx[k] = (uint32_t)ctx | (cls << 16); sof[k] = incl - nb; spi[k] = old + (uint32_t)__popc(m & lt); }
+                    if (lane == 31) S.ctot[c] = incl;
                 }
-                if (lane == 31) S.ctot[c] = incl;
             }
             __syncthreads();
             PHASE_MARK(0);
@@ -410,56 +420,63 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
             }
             PHASE_MARK(1);
 
+            // ---- class lists: class q's samples start at cb_q (classes back to back, warps in order inside a class, x order inside
+            // a warp's share); every warp works the layout out for itself from the [class][warp] counts, then scatters the samples
+            // it prepared. A sample's record offset is relative to its column segment.
+            uint32_t klo, khi;
+            {
+                uint32_t before = 0, tot = 0;
+                if (lane < NW) {
+                    const uint32_t* row = reinterpret_cast<const uint32_t*>(S.wcnt + lane * NW);
+#pragma unroll
+                    for (int w2 = 0; w2 < NW / 2; w2++) {
+                        const uint32_t pr = row[w2], lo = pr & 0xFFFFu, hi = pr >> 16;
+                        tot += lo + hi;
+                        if (2 * w2 < warp) before += lo;
+                        if (2 * w2 + 1 < warp) before += hi;
+                    }
+                }
+                uint32_t inc = tot;
+#pragma unroll
+                for (int o = 1; o < NW; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                const uint32_t cbq = inc - tot, cstart = cbq + before;
+                klo = __shfl_sync(0xffffffffu, cbq, warp & 31);
+                khi = klo + __shfl_sync(0xffffffffu, tot, warp & 31);
+#pragma unroll
+                for (int k = 0; k < KCMAX; k++) {
+                    const int c = warp * KC + k;
+                    if (k < KC && c < nchunk) {
+                        const uint32_t st0 = __shfl_sync(0xffffffffu, cstart, (scx[k] >> 16) & 31u);
+                        int sg = 0;
+                        while (sg + 1 < nsg && c >= sc[sg + 1]) sg++;
+                        const uint32_t relc = (sg == 0 ? seg_extra : 0u) + chunk_base(c) - chunk_base(sc[sg]);
+                        if (scx[k] != 0xFFFFFFFFu)
+                            S.ent[st0 + spi[k]] = make_uint2(((uint32_t)sv[k] & 0x3FFFFu) | ((uint32_t)(c * 32 + lane) << 18),
+                                                             (scx[k] & 0xFFFFu) | ((relc + sof[k]) << 16));
+                    }
+                }
+            }
+            __syncthreads();
+            uint32_t kcur = klo;             // next sample of my class (the cursor runs on over the column segments)
             const uint32_t rc_base = ((uint32_t)(fs * A.band_rows + (y - r0)) * 3u + (uint32_t)(ps ? 1 + pl : 0)) * (uint32_t)A.nseg;
             for (int s = 0; s < nsg; s++) {
                 const int c0 = sc[s], c1 = sc[s + 1];
                 const uint32_t extra = s == 0 ? seg_extra : 0u;
                 const uint32_t segbase = chunk_base(c0);
                 const uint32_t seg_total = extra + chunk_base(c1) - segbase;
-                const uint32_t rel = extra - segbase;          // record offset of a sample = rel + chunk base + off[x]
                 // ---- S2 (K3): warp q = context class q. Its samples of this segment, in x order, 32 per batch.
                 {
-                    // masks of my class: lane l holds chunks l and l + 32
-                    const bool in0 = lane >= c0 && lane < c1, in1 = lane + 32 >= c0 && lane + 32 < c1;
-                    const uint32_t M0 = in0 ? S.cmask[lane * NW + warp] : 0u, M1 = in1 ? S.cmask[(lane + 32) * NW + warp] : 0u;
-                    if (in0) S.cmask[lane * NW + warp] = 0;
-                    if (in1) S.cmask[(lane + 32) * NW + warp] = 0;
-                    const uint32_t n0 = __popc(M0), n1 = __popc(M1);
-                    uint32_t q0 = n0, q1 = n1;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t a0 = __shfl_up_sync(0xffffffffu, q0, o), a1 = __shfl_up_sync(0xffffffffu, q1, o);
-                        if (lane >= o) { q0 += a0; q1 += a1; }
-                    }
-                    const uint32_t cnt0 = __shfl_sync(0xffffffffu, q0, 31);
-                    const uint32_t P0 = q0 - n0, P1 = cnt0 + q1 - n1;           // samples of my class before chunk l / l + 32
-                    const uint32_t mine = cnt0 + __shfl_sync(0xffffffffu, q1, 31);
-                    for (uint32_t b0 = 0; b0 < mine; b0 += 32) {
-                        const uint32_t k = b0 + lane;
-                        const bool have = k < mine;
-                        // the chunk of sample k: the last chunk whose prefix is <= k (binary search over the 64 prefixes)
-                        uint32_t c = 0;
-#pragma unroll
-                        for (int st = 32; st; st >>= 1) {
-                            const uint32_t t = c + st;
-                            const uint32_t p0 = __shfl_sync(0xffffffffu, P0, t & 31), p1 = __shfl_sync(0xffffffffu, P1, t & 31);
-                            const uint32_t pt = t < 32 ? p0 : p1;
-                            if (t < 64 && pt <= k) c = t;
-                        }
-                        const uint32_t m0 = __shfl_sync(0xffffffffu, M0, c & 31), m1 = __shfl_sync(0xffffffffu, M1, c & 31);
-                        const uint32_t pc0 = __shfl_sync(0xffffffffu, P0, c & 31), pc1 = __shfl_sync(0xffffffffu, P1, c & 31);
-                        const uint32_t e0 = __shfl_sync(0xffffffffu, ex0, c & 31), e1 = __shfl_sync(0xffffffffu, ex1, c & 31);
-                        uint32_t mc = c < 32 ? m0 : m1;
-                        uint32_t r = k - (c < 32 ? pc0 : pc1);
-                        int v = 0;
-                        uint32_t cx = 0x10000u + (uint32_t)lane, o = 0;
-                        if (have) {
-                            while (r) { mc &= mc - 1; r--; }
-                            const int x = (int)(c * 32u) + __ffs(mc) - 1;
-                            v = S.val[x];
-                            cx = S.ctx[x];
-                            o = rel + (c < 32 ? e0 : e1) + S.off[x];
-                        }
+                    for (;;) {
+                        const uint32_t idx = kcur + (uint32_t)lane;
+                        bool have = idx < khi;
+                        uint2 en = make_uint2(0u, 0u);
+                        if (have) en = S.ent[idx];
+                        have = have && (int)(en.x >> 23) < c1;                   // chunk of the sample = x >> 5: still in this segment?
+                        const uint32_t hmask = __ballot_sync(0xffffffffu, have);
+                        if (!hmask) break;
+                        const int v = have ? ((int)(en.x << 14)) >> 14 : 0;
+                        const uint32_t cx = have ? (en.y & 0xFFFFu) : 0x10000u + (uint32_t)lane;
+                        const uint32_t o = en.y >> 16;
                         // rounds: samples of the batch that share a context go one after the other
                         const uint32_t mm = __match_any_sync(0xffffffffu, cx);
                         const int rank = __popc(mm & lt);
@@ -517,7 +534,11 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                 const int kA = lane == 0 ? 0 : isB ? lane : isD ? 2 : 23 - lane;
                                 const uint32_t ee = (uint32_t)(e < 0 ? 0 : e);
                                 const uint32_t ow = (2u * o) | ((2u * o + 4u * ee) << 16);
-                                const uint32_t abase = stage_a + 2u * (uint32_t)kA, hs = (lane == 0 || isB) ? 0u : 16u, lbit = 1u << lane;
+                                // lane constants of the sample loop, pinned in registers (the compiler would otherwise rebuild them from the
+                                // lane number in every iteration): stage address of my bin, which half of `ow` I take, my slot's bit
+                                uint32_t abase = stage_a + 2u * (uint32_t)kA, hsel = (lane == 0 || isB) ? 0x4410u : 0x4432u, lbit = 1u << lane;
+                                uint32_t tr0 = trans_a;
+                                asm volatile("" : "+r"(abase), "+r"(hsel), "+r"(lbit), "+r"(tr0));
                                 uint32_t leaders = __ballot_sync(0xffffffffu, chain && rank == 0);
                                 while (leaders) {
                                     const int L = __ffs(leaders) - 1;
@@ -526,18 +547,27 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                     const uint32_t cj = __shfl_sync(0xffffffffu, cx, L);
                                     const uint32_t sp = states_a + cj * (uint32_t)kRow + (uint32_t)lslot;
                                     uint32_t st = lane_has_slot ? lds_u8_volatile(sp) : 128u;
-                                    while (members) {
-                                        const int j = __ffs(members) - 1;
-                                        members &= members - 1;
-                                        const uint32_t umj = __shfl_sync(0xffffffffu, um, j), bmj = __shfl_sync(0xffffffffu, bmk, j);
-                                        const uint32_t owj = __shfl_sync(0xffffffffu, ow, j);
-                                        const bool bit = (bmj & lbit) != 0;
-                                        const int s1 = bit ? 1 : -1;
-                                        const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                        if (umj & lbit) {
-                                            sts_u16(abase + ((owj >> hs) & 0xFFFFu), rec);
-                                            st = lds_u8(trans_a + st + (bit ? 256u : 0u));
+                                    // the sample loop is software-pipelined: the three words of the next sample are on their way while this
+                                    // one's bin is coded, so that the only latency from sample to sample is the (bit, state) look-up
+                                    int j = __ffs(members) - 1;
+                                    members &= members - 1;
+                                    uint32_t umn = __shfl_sync(0xffffffffu, um, j), bmn = __shfl_sync(0xffffffffu, bmk, j), own = __shfl_sync(0xffffffffu, ow, j);
+                                    for (;;) {
+                                        const uint32_t umj = umn, bmj = bmn, owj = own;
+                                        const bool more = members != 0;                    // warp-uniform
+                                        if (more) {
+                                            j = __ffs(members) - 1;
+                                            members &= members - 1;
+                                            umn = __shfl_sync(0xffffffffu, um, j); bmn = __shfl_sync(0xffffffffu, bmk, j); own = __shfl_sync(0xffffffffu, ow, j);
                                         }
+                                        const uint32_t used = umj & lbit, bitm = bmj & lbit;
+                                        const uint32_t rec = bitm ? 255u + st : 255u - st;
+                                        const uint32_t dst = abase + __byte_perm(owj, 0, hsel);
+                                        const uint32_t ta = tr0 + st + (bitm ? 256u : 0u);
+                                        // predicated, not branched: lanes whose slot the sample does not use keep their state
+                                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u16 [%1], %2;\n\t@p ld.shared.u8 %0, [%4];\n\t}"
+                                                     : "+r"(st) : "r"(dst), "h"((uint16_t)rec), "r"(used), "r"(ta) : "memory");
+                                        if (!more) break;
                                     }
                                     if (lane_has_slot) sts_u8(sp, st);
                                 }
@@ -665,6 +695,8 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                             }
                             __syncwarp();       // the next round / batch reads the state rows this one wrote
                         }
+                        kcur += (uint32_t)__popc(hmask);
+                        if (hmask != 0xffffffffu) break;
                     }
                 }
                 // no-op records up to the next whole block
