@@ -86,8 +86,10 @@ constexpr uint32_t kNopRec = 0x00FFu;
 //   qtab    5 x 256 int16    quantisation tables
 //   t1      one_state, indexed by q: either replicated per bank ([64][32] words: lane l reads word (q >> 2) * 32 + l, no
 //           bank conflicts whatever the 32 lanes look up) or a plain 256-byte table when shared memory is short
-//   ent     the samples of the plane-row being coded, grouped by context class (= owner warp), x order inside a class: folded
-//           residual (after the context-sign flip) | x << 18, context | first record of the sample in the stage << 16
+//   ent     the samples of the plane-row being coded, grouped by context class (= owner warp), x order inside a class, 16 bytes
+//           each: slots the symbol uses (bit mask), value of the bin of each slot (bit mask), byte offsets of its records in the
+//           stage (2o | (2o + 4e) << 16), folded residual (after the context-sign flip, 18 bits) | context << 18
+//   segcnt  [segment][class] samples of the class in a column segment (only when a plane-row needs more than one segment)
 //   ctot    records per 32-sample chunk
 //   wcnt    [class][warp] samples of the class among the chunks that warp prepared in S1
 //   stage   the records of the plane-row (segment), 16 bit each, split into q bytes + bit-plane on the way out
@@ -100,7 +102,7 @@ constexpr uint32_t kNopRec = 0x00FFu;
 // barrier inside S2.
 struct ModelSmem {
     uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b;
-    uint2* ent; uint32_t* ctot; uint16_t* wcnt; uint32_t* misc; uint8_t* tpow; uint8_t* trans; uint16_t* stage;
+    uint4* ent; uint32_t* ctot; uint16_t* wcnt; uint32_t* segcnt; uint32_t* misc; uint8_t* tpow; uint8_t* trans; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -111,10 +113,11 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int t1_rep)
     n += align16((size_t)3 * planes * wmax * 4);
     n += 5 * 256 * 2;
     n += rep ? 64 * 32 * 4 : 256;
-    n += align16((size_t)wmax * 8);          // ent
+    n += (size_t)wmax * 16;                  // ent
     const int nch = (wmax + 31) / 32;
     n += align16((size_t)nch * 4);           // ctot
     n += align16((size_t)kModelWarps * kModelWarps * 2);      // wcnt
+    n += (size_t)kMaxSeg * kModelWarps * 4;  // segcnt
     n += kModelWarps * 64;                   // misc: per-lane landing place of the records of idle lanes
     n += 5 * 256;                            // tpow
     n += 512;                                // trans
@@ -131,10 +134,11 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     m.ring = reinterpret_cast<int32_t*>(base); base += align16((size_t)3 * planes * wmax * 4);
     m.qtab = reinterpret_cast<int16_t*>(base); base += 5 * 256 * 2;
     m.t1w = reinterpret_cast<uint32_t*>(base); m.t1b = base; base += rep ? 64 * 32 * 4 : 256;
-    m.ent = reinterpret_cast<uint2*>(base); base += align16((size_t)wmax * 8);
+    m.ent = reinterpret_cast<uint4*>(base); base += (size_t)wmax * 16;
     const int nch = (wmax + 31) / 32;
     m.ctot = reinterpret_cast<uint32_t*>(base); base += align16((size_t)nch * 4);
     m.wcnt = reinterpret_cast<uint16_t*>(base); base += align16((size_t)kModelWarps * kModelWarps * 2);
+    m.segcnt = reinterpret_cast<uint32_t*>(base); base += (size_t)kMaxSeg * kModelWarps * 4;
     m.misc = reinterpret_cast<uint32_t*>(base); base += kModelWarps * 64;
     m.tpow = base; base += 5 * 256;
     m.trans = base; base += 512;
@@ -167,6 +171,11 @@ __host__ __device__ constexpr int cslot(int slot) { return kCompact ? slot - (sl
 // shared-memory accesses by 32-bit shared address (no generic-address conversion per access)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u8_volatile(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
@@ -320,6 +329,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
             // them in registers until the class lists can be laid out (after the barrier)
             constexpr int KCMAX = (2048 / 32 + NW - 1) / NW;                       // wmax <= 2048
             if (lane < NW) S.wcnt[lane * NW + warp] = 0;
+            if (tid < kMaxSeg * NW) S.segcnt[tid] = 0;
             __syncwarp();
             int sv[KCMAX];
             uint32_t scx[KCMAX], sof[KCMAX], spi[KCMAX];   // context | class << 16 (all ones: no sample), first record within the chunk, rank among my warp's samples of the class
@@ -450,9 +460,26 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                         int sg = 0;
                         while (sg + 1 < nsg && c >= sc[sg + 1]) sg++;
                         const uint32_t relc = (sg == 0 ? seg_extra : 0u) + chunk_base(c) - chunk_base(sc[sg]);
-                        if (scx[k] != 0xFFFFFFFFu)
-                            S.ent[st0 + spi[k]] = make_uint2(((uint32_t)sv[k] & 0x3FFFFu) | ((uint32_t)(c * 32 + lane) << 18),
-                                                             (scx[k] & 0xFFFFu) | ((relc + sof[k]) << 16));
+                        if (nsg > 1) {                   // samples of each class per column segment
+                            const uint32_t m2 = __match_any_sync(0xffffffffu, scx[k] != 0xFFFFFFFFu ? scx[k] >> 16 : 32u + (uint32_t)lane);
+                            if (scx[k] != 0xFFFFFFFFu && (m2 & lt) == 0) atomicAdd(&S.segcnt[sg * NW + (int)(scx[k] >> 16)], (uint32_t)__popc(m2));
+                        }
+                        if (scx[k] != 0xFFFFFFFFu) {
+                            // what the symbol does to the 32 slots of its context (rangecoder::s, FFV1_RangeCoder.cpp:135-171): slot 0 zero
+                            // flag | 1..10 exponent | 11..21 sign | 22..31 mantissa. Symbols with exponent > 9 use slots 10 and 31 more than
+                            // once; they never take the mask-driven path.
+                            const int v = sv[k];
+                            const uint32_t a = (uint32_t)abs(v);
+                            const int e = v ? 31 - __clz(a) : 0;
+                            uint32_t um = 1u, bmk = v ? 0u : 1u;
+                            if (v && e <= 9) {
+                                const uint32_t le = (1u << e) - 1u;
+                                um = 1u | ((((1u << (e + 1)) - 1u)) << 1) | (1u << (11 + e)) | (le << 22);
+                                bmk = (le << 1) | ((v < 0 ? 1u : 0u) << (11 + e)) | ((a & le) << 22);
+                            }
+                            const uint32_t o2 = 2u * (relc + sof[k]);
+                            S.ent[st0 + spi[k]] = make_uint4(um, bmk, o2 | ((o2 + 4u * (uint32_t)e) << 16), ((uint32_t)v & 0x3FFFFu) | ((scx[k] & 0xFFFFu) << 18));
+                        }
                     }
                 }
             }
@@ -466,17 +493,17 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 const uint32_t seg_total = extra + chunk_base(c1) - segbase;
                 // ---- S2 (K3): warp q = context class q. Its samples of this segment, in x order, 32 per batch.
                 {
+                    const uint32_t kend = nsg == 1 ? khi : kcur + S.segcnt[s * NW + warp];
                     for (;;) {
                         const uint32_t idx = kcur + (uint32_t)lane;
-                        bool have = idx < khi;
-                        uint2 en = make_uint2(0u, 0u);
-                        if (have) en = S.ent[idx];
-                        have = have && (int)(en.x >> 23) < c1;                   // chunk of the sample = x >> 5: still in this segment?
+                        const bool have = idx < kend;
                         const uint32_t hmask = __ballot_sync(0xffffffffu, have);
                         if (!hmask) break;
-                        const int v = have ? ((int)(en.x << 14)) >> 14 : 0;
-                        const uint32_t cx = have ? (en.y & 0xFFFFu) : 0x10000u + (uint32_t)lane;
-                        const uint32_t o = en.y >> 16;
+                        uint4 en = make_uint4(1u, 1u, 0u, 0u);
+                        if (have) en = S.ent[idx];
+                        const int v = ((int)(en.w << 14)) >> 14;
+                        const uint32_t cx = have ? (en.w >> 18) : 0x10000u + (uint32_t)lane;
+                        const uint32_t o = (en.z & 0xFFFFu) >> 1;
                         // rounds: samples of the batch that share a context go one after the other
                         const uint32_t mm = __match_any_sync(0xffffffffu, cx);
                         const int rank = __popc(mm & lt);
@@ -523,22 +550,28 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                             if (bigm) {
                                 // a group is chained only if none of its members has e > 9
                                 const bool chain = big && (mm & wide) == 0;
-                                uint32_t um = 1u, bmk = nz ? 0u : 1u;
-                                if (nz && e <= 9) {
-                                    const uint32_t le = (1u << e) - 1u;
-                                    um = 1u | ((((1u << (e + 1)) - 1u)) << 1) | (1u << (11 + e)) | (le << 22);
-                                    bmk = (le << 1) | ((neg ? 1u : 0u) << (11 + e)) | ((a & le) << 22);
-                                }
                                 // record index of my slot's bin inside a symbol of exponent e: kA + kE * e with kE = 0 (zero flag,
-                                // exponent) or 2 (sign, mantissa): the sample hands over both byte offsets, 2o and 2o + 4e, in one word
+                                // exponent) or 2 (sign, mantissa): a sample's entry holds both byte offsets, 2o and 2o + 4e, in one word.
+                                // Lane constants of the sample loop, pinned in registers (the compiler would otherwise rebuild them from
+                                // the lane number in every iteration): stage address of my bin, which half of the offset word I take, my
+                                // slot's bit, the two halves of the (bit, state) table
                                 const int kA = lane == 0 ? 0 : isB ? lane : isD ? 2 : 23 - lane;
-                                const uint32_t ee = (uint32_t)(e < 0 ? 0 : e);
-                                const uint32_t ow = (2u * o) | ((2u * o + 4u * ee) << 16);
-                                // lane constants of the sample loop, pinned in registers (the compiler would otherwise rebuild them from the
-                                // lane number in every iteration): stage address of my bin, which half of `ow` I take, my slot's bit
                                 uint32_t abase = stage_a + 2u * (uint32_t)kA, hsel = (lane == 0 || isB) ? 0x4410u : 0x4432u, lbit = 1u << lane;
-                                uint32_t tr0 = trans_a;
-                                asm volatile("" : "+r"(abase), "+r"(hsel), "+r"(lbit), "+r"(tr0));
+                                uint32_t tr0 = trans_a, tr1 = trans_a + 256u;
+                                asm volatile("" : "+r"(abase), "+r"(hsel), "+r"(lbit), "+r"(tr0), "+r"(tr1));
+                                const uint32_t eb = smem_addr(S.ent) + kcur * 16u;            // the batch's entries, lane order
+                                // one sample of the chain: its entry (slots used, bin values, record offsets) was read from shared
+                                // memory (same address for every lane) two samples earlier; lanes whose slot the symbol does not use keep
+                                // their state (predicated, not branched), so the only latency from sample to sample is the (bit, state)
+                                // look-up of the slots in use
+                                auto chain_step = [&](const uint4& E, uint32_t& st) {
+                                    const uint32_t used = E.x & lbit, bitm = E.y & lbit;
+                                    const uint32_t rec = bitm ? 255u + st : 255u - st;
+                                    const uint32_t dst = abase + __byte_perm(E.z, 0, hsel);
+                                    const uint32_t ta = (bitm ? tr1 : tr0) + st;
+                                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u16 [%1], %2;\n\t@p ld.shared.u8 %0, [%4];\n\t}"
+                                                 : "+r"(st) : "r"(dst), "h"((uint16_t)rec), "r"(used), "r"(ta) : "memory");
+                                };
                                 uint32_t leaders = __ballot_sync(0xffffffffu, chain && rank == 0);
                                 while (leaders) {
                                     const int L = __ffs(leaders) - 1;
@@ -547,27 +580,20 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                     const uint32_t cj = __shfl_sync(0xffffffffu, cx, L);
                                     const uint32_t sp = states_a + cj * (uint32_t)kRow + (uint32_t)lslot;
                                     uint32_t st = lane_has_slot ? lds_u8_volatile(sp) : 128u;
-                                    // the sample loop is software-pipelined: the three words of the next sample are on their way while this
-                                    // one's bin is coded, so that the only latency from sample to sample is the (bit, state) look-up
-                                    int j = __ffs(members) - 1;
-                                    members &= members - 1;
-                                    uint32_t umn = __shfl_sync(0xffffffffu, um, j), bmn = __shfl_sync(0xffffffffu, bmk, j), own = __shfl_sync(0xffffffffu, ow, j);
+                                    int n = __popc(members);
+                                    int j = 0;
+                                    auto next_entry = [&]() -> uint4 {       // entry of the next member (the last one again once they are used up)
+                                        if (members) { j = __ffs(members) - 1; members &= members - 1; }
+                                        return lds_v4(eb + (uint32_t)j * 16u);
+                                    };
+                                    uint4 EA = next_entry(), EB = next_entry();
                                     for (;;) {
-                                        const uint32_t umj = umn, bmj = bmn, owj = own;
-                                        const bool more = members != 0;                    // warp-uniform
-                                        if (more) {
-                                            j = __ffs(members) - 1;
-                                            members &= members - 1;
-                                            umn = __shfl_sync(0xffffffffu, um, j); bmn = __shfl_sync(0xffffffffu, bmk, j); own = __shfl_sync(0xffffffffu, ow, j);
-                                        }
-                                        const uint32_t used = umj & lbit, bitm = bmj & lbit;
-                                        const uint32_t rec = bitm ? 255u + st : 255u - st;
-                                        const uint32_t dst = abase + __byte_perm(owj, 0, hsel);
-                                        const uint32_t ta = tr0 + st + (bitm ? 256u : 0u);
-                                        // predicated, not branched: lanes whose slot the sample does not use keep their state
-                                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u16 [%1], %2;\n\t@p ld.shared.u8 %0, [%4];\n\t}"
-                                                     : "+r"(st) : "r"(dst), "h"((uint16_t)rec), "r"(used), "r"(ta) : "memory");
-                                        if (!more) break;
+                                        chain_step(EA, st);
+                                        EA = next_entry();
+                                        if (--n == 0) break;
+                                        chain_step(EB, st);
+                                        EB = next_entry();
+                                        if (--n == 0) break;
                                     }
                                     if (lane_has_slot) sts_u8(sp, st);
                                 }
@@ -855,11 +881,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t lds_u16v(uint32_t a) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
