@@ -155,6 +155,10 @@ constexpr int kDenseMin = B200_DENSE_MIN;        // rounds with fewer samples th
 #define B200_CHAIN_MIN 3       // measured on B200 (ms per 64 grainy 4K frames): 2 -> 192, 3 -> 193, 5 -> 199, 8 -> 205; low-noise content is indifferent
 #endif
 constexpr int kChainMin = B200_CHAIN_MIN;      // a context with at least this many samples in a batch is coded as a chain
+#ifndef B200_CHAIN_SCAN
+#define B200_CHAIN_SCAN 12
+#endif
+constexpr int kChainScan = B200_CHAIN_SCAN;    // chains of at least this many samples walk the whole batch instead of searching for their members
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
@@ -581,6 +585,22 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                     const uint32_t sp = states_a + cj * (uint32_t)kRow + (uint32_t)lslot;
                                     uint32_t st = lane_has_slot ? lds_u8_volatile(sp) : 128u;
                                     int n = __popc(members);
+                                    if (n >= kChainScan) {
+                                        // a long chain (a hot context takes most of the batch): walk all 32 entries of the batch in order,
+                                        // entry j + 2 on its way while entry j is coded, and skip the ones of other contexts with a
+                                        // warp-uniform test: no bit search, no address arithmetic, nothing but the look-up in the way
+                                        uint4 E0 = lds_v4(eb), E1 = lds_v4(eb + 16u);
+#pragma unroll
+                                        for (int jj = 0; jj < 32; jj += 2) {
+                                            const uint4 F0 = E0, F1 = E1;
+                                            if (jj + 2 < 32) E0 = lds_v4(eb + (uint32_t)(jj + 2) * 16u);
+                                            if (jj + 3 < 32) E1 = lds_v4(eb + (uint32_t)(jj + 3) * 16u);
+                                            if (members & (1u << jj)) chain_step(F0, st);
+                                            if (members & (2u << jj)) chain_step(F1, st);
+                                        }
+                                        if (lane_has_slot) sts_u8(sp, st);
+                                        continue;
+                                    }
                                     int j = 0;
                                     auto next_entry = [&]() -> uint4 {       // entry of the next member (the last one again once they are used up)
                                         if (members) { j = __ffs(members) - 1; members &= members - 1; }
