@@ -11,6 +11,7 @@
 #include "ffv1_kernels.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "../../include/b200enc.h"
 
@@ -155,6 +156,9 @@ constexpr int kDenseMin = B200_DENSE_MIN;        // rounds with fewer samples th
 #define B200_CHAIN_MIN 3       // measured on B200 (ms per 64 grainy 4K frames): 2 -> 192, 3 -> 193, 5 -> 199, 8 -> 205; low-noise content is indifferent
 #endif
 constexpr int kChainMin = B200_CHAIN_MIN;      // a context with at least this many samples in a batch is coded as a chain
+#ifndef B200_SERIAL_S2
+#define B200_SERIAL_S2 1        // 1: the class warps code their samples one after the other, one lane per slot; 0: batches of 32 (zero runs, chains, rank rounds)
+#endif
 #ifndef B200_CHAIN_SCAN
 #define B200_CHAIN_SCAN 12
 #endif
@@ -208,6 +212,36 @@ __device__ __forceinline__ void slot_step(const uint32_t (&S0)[8], uint32_t (&S)
     const uint32_t ins = __byte_perm(S[wi], nx, bi == 0 ? 0x3214 : bi == 1 ? 0x3240 : bi == 2 ? 0x3410 : 0x4210);
     S[wi] = used ? ins : S[wi];
     sts_u16(used ? dst : dummy, rec);
+}
+
+
+// A symbol with exponent > 9 on the one-lane-per-slot path: slots 10 and 31 take several bins of the symbol; lane s runs the bins
+// of its slot on the state it holds and returns the new state (rangecoder::s, FFV1_RangeCoder.cpp:135-171). Rare (|residual| >=
+// 1024), kept out of line so that the sample loop stays small.
+__device__ __noinline__ uint32_t wide_symbol(const uint4 E, uint32_t st, int lane, uint32_t stage_a, uint32_t trans_a) {
+    const int vj = ((int)(E.w << 14)) >> 14;
+    const uint32_t ob = (E.z & 0xFFFFu) >> 1;
+    const uint32_t aj = (uint32_t)abs(vj);
+    const int ej = 31 - __clz(aj | 1);
+    int n2 = 0, i0b = 0, step = 0;     // n2 bins; bin k uses index i = i0b + k*step
+    if (lane == 0) n2 = 1;
+    else if (lane <= 9) { n2 = 1; i0b = lane - 1; }
+    else if (lane == 10) { n2 = ej - 8; i0b = 9; step = 1; }
+    else if (lane <= 21) { n2 = (lane - 11) == min(ej, 10); }
+    else if (lane <= 30) { n2 = 1; i0b = lane - 22; }
+    else { n2 = ej - 9; i0b = ej - 1; step = -1; }
+    for (int kk = 0; kk < n2; kk++) {
+        const int i = i0b + kk * step;
+        bool bit; uint32_t bidx;
+        if (lane == 0) { bit = false; bidx = 0; }
+        else if (lane <= 10) { bit = i < ej; bidx = 1 + i; }
+        else if (lane <= 21) { bit = vj < 0; bidx = 2 * ej + 2; }
+        else { bit = ((aj >> i) & 1u) != 0; bidx = 2 * ej + 1 - i; }
+        const uint32_t rec = bit ? 255u + st : 255u - st;
+        sts_u16(stage_a + (ob + bidx) * 2u, rec);
+        st = lds_u8(trans_a + st + (bit ? 256u : 0u));
+    }
+    return st;
 }
 
 template <bool kCompact, bool kRep>
@@ -480,7 +514,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                                 const uint32_t le = (1u << e) - 1u;
                                 um = 1u | ((((1u << (e + 1)) - 1u)) << 1) | (1u << (11 + e)) | (le << 22);
                                 bmk = (le << 1) | ((v < 0 ? 1u : 0u) << (11 + e)) | ((a & le) << 22);
-                            }
+                            } else if (v) um = 0u;            // no mask for this one
                             const uint32_t o2 = 2u * (relc + sof[k]);
                             S.ent[st0 + spi[k]] = make_uint4(um, bmk, o2 | ((o2 + 4u * (uint32_t)e) << 16), ((uint32_t)v & 0x3FFFFu) | ((scx[k] & 0xFFFFu) << 18));
                         }
@@ -498,6 +532,91 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 // ---- S2 (K3): warp q = context class q. Its samples of this segment, in x order, 32 per batch.
                 {
                     const uint32_t kend = nsg == 1 ? khi : kcur + S.segcnt[s * NW + warp];
+#if B200_SERIAL_S2
+                    // The samples of my class go one after the other, in list (= bitstream) order; lane s holds the state of slot s of
+                    // the context being coded. What a symbol does to the 32 slots comes as the two masks S1 left in its entry (slot
+                    // used / bin value), read from shared memory two samples ahead (same address for every lane); lanes whose slot
+                    // the symbol does not use keep their state (predicated, not branched). A sample costs about twenty instructions
+                    // whatever its context did before: consecutive samples of one context (low-noise and flat content: a handful of
+                    // contexts take most of a row) pay one (bit, state) look-up of latency each, a change of context one store and
+                    // one load of the 32 state bytes.
+                    {
+                        const int kA = lane == 0 ? 0 : isB ? lane : isD ? 2 : 23 - lane;     // record index of my slot's bin: kA + kE e, kE = 0 or 2
+                        uint32_t abase = stage_a + 2u * (uint32_t)kA, hsel = (lane == 0 || isB) ? 0x4410u : 0x4432u, lbit = 1u << lane;
+                        uint32_t tr0 = trans_a, tr1 = trans_a + 256u;
+                        uint32_t srow = states_a + (uint32_t)lslot;
+                        asm volatile("" : "+r"(abase), "+r"(hsel), "+r"(lbit), "+r"(tr0), "+r"(tr1), "+r"(srow));
+                        // lanes without a slot (8-bit streams: 27 states per context) and the time before the first context use a
+                        // landing byte of their own, so that the loads and stores of the state bytes need no further condition
+                        const uint32_t spare = smem_addr(S.misc) + (uint32_t)warp * 64u + (uint32_t)lane;
+                        uint32_t cur = 0xFFFFFFFFu, st = 128u, sp = spare;
+                        auto flush = [&]() { sts_u8(sp, st); cur = 0xFFFFFFFFu; sp = spare; };
+                        // kWide: the batch holds symbols with exponent > 9 (no masks: entry.x == 0), coded out of line
+                        auto sample_step = [&](const uint4& E, auto wide_tag) {
+                            constexpr bool kWide = decltype(wide_tag)::value;
+                            const uint32_t cxs = E.w >> 18;
+                            const uint32_t spn = lane_has_slot ? srow + cxs * (uint32_t)kRow : spare;
+                            // change of context (warp-wide, predicated): the state bytes go back, the new context's come in
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, %4;\n\t@p st.shared.u8 [%1], %0;\n\t@p ld.shared.u8 %0, [%2];\n\t}"
+                                         : "+r"(st) : "r"(sp), "r"(spn), "r"(cxs), "r"(cur) : "memory");
+                            sp = spn;
+                            cur = cxs;
+                            if (!kWide || E.x != 0u) {
+                                const uint32_t used = E.x & lbit, bitm = E.y & lbit;
+                                const uint32_t ta = (bitm ? tr1 : tr0) + st;
+                                const uint32_t rec = bitm ? 255u + st : 255u - st;
+                                const uint32_t dst = abase + __byte_perm(E.z, 0, hsel);
+                                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.u8 %0, [%4];\n\t@p st.shared.u16 [%1], %2;\n\t}"
+                                             : "+r"(st) : "r"(dst), "h"((uint16_t)rec), "r"(used), "r"(ta) : "memory");
+                            } else {
+                                st = wide_symbol(E, st, lane, stage_a, trans_a);
+                            }
+                        };
+                        while (kcur < kend) {
+                            const uint32_t nbt = min(32u, kend - kcur);
+                            const bool have = (uint32_t)lane < nbt;
+                            uint4 en = make_uint4(1u, 1u, 0u, 0u);
+                            if (have) en = S.ent[kcur + (uint32_t)lane];
+                            const uint32_t cx0 = __shfl_sync(0xffffffffu, en.w >> 18, 0);
+                            // runs of zeros: when every sample of the batch has residual 0 and they share a context (flat areas, mattes,
+                            // black frames), the k-th of them sees state one_state^k(st) of slot 0 and nothing else moves: all of them
+                            // at once, through the tables of one_state^(2^i)
+                            if (__all_sync(0xffffffffu, !have || ((en.w & 0x3FFFFu) == 0u && (en.w >> 18) == cx0))) {
+                                if (cur == cx0) flush();                               // the zero run works on the state row in shared memory
+                                __syncwarp();
+                                const uint32_t sa = states_a + cx0 * (uint32_t)kRow;          // slot 0 = byte 0 of the row
+                                uint32_t z0 = lds_u8_volatile(sa);
+                                __syncwarp();
+#pragma unroll
+                                for (int kk = 0; kk < 5; kk++)
+                                    if ((lane >> kk) & 1) z0 = lds_u8(tpow_a + kk * 256 + z0);
+                                if (have) sts_u16(stage_a + (en.z & 0xFFFFu), z0 + 255u);                             // q = st - 1, bit 1
+                                if ((uint32_t)lane == nbt - 1u) sts_u8(sa, lds_u8(tpow_a + z0));
+                                __syncwarp();
+                            } else {
+                                // each entry is asked for one sample ahead of its use (right after its register set has been consumed)
+                                const uint32_t ea = smem_addr(S.ent) + kcur * 16u;
+                                const bool anywide = __any_sync(0xffffffffu, have && en.x == 0u);
+                                auto walk = [&](auto wide_tag) {
+                                    uint4 E0 = lds_v4(ea), E1 = lds_v4(ea + 16u);          // (past the end of the list: still shared memory, unused)
+                                    uint32_t off = 32u;
+                                    const uint32_t pairs = nbt >> 1;
+                                    for (uint32_t jj = 0; jj < pairs; jj++, off += 32u) {
+                                        sample_step(E0, wide_tag);
+                                        E0 = lds_v4(ea + off);
+                                        sample_step(E1, wide_tag);
+                                        E1 = lds_v4(ea + off + 16u);
+                                    }
+                                    if (nbt & 1u) sample_step(E0, wide_tag);
+                                };
+                                if (anywide) walk(std::true_type{}); else walk(std::false_type{});
+                            }
+                            kcur += nbt;
+                        }
+                        flush();
+                        __syncwarp();
+                    }
+#else
                     for (;;) {
                         const uint32_t idx = kcur + (uint32_t)lane;
                         const bool have = idx < kend;
@@ -744,6 +863,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                         kcur += (uint32_t)__popc(hmask);
                         if (hmask != 0xffffffffu) break;
                     }
+#endif
                 }
                 // no-op records up to the next whole block
                 const uint32_t padded = (seg_total + (uint32_t)kBlockRecs - 1u) & ~((uint32_t)kBlockRecs - 1u);
