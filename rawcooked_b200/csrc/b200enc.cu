@@ -302,6 +302,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
                 if (parted) {
                     A.model_ctas = E->part.sm_count(last);
                     A.range_smem = 120 * 1024;           // one k_range CTA per SM of its partition
+                    if (const char* e = getenv("B200_RANGE_CTAS_PER_SM")) { int v = atoi(e); if (v >= 2) A.range_smem = 0; }
                     A.range_sms = E->part.sm_count(0);
                     for (int pz = 1; pz < E->kpar; pz++) {
                         E->argsN[pz].model_ctas = A.model_ctas; E->argsN[pz].range_smem = A.range_smem; E->argsN[pz].range_sms = A.range_sms;

@@ -1028,12 +1028,16 @@ __device__ __forceinline__ uint32_t lds_u16v(uint32_t a) {
 }
 
 constexpr int kRangeWarps = 4;                       // one per scheduler
-constexpr int kRangeSlots = 4;                       // blocks in a lane's ring: one being read, two on their way, one just read
+#ifndef B200_RANGE_SLOTS
+#define B200_RANGE_SLOTS 4
+#endif
+constexpr int kRangeSlots = B200_RANGE_SLOTS;        // blocks in a lane's ring: one being read, kRangeSlots - 2 on their way, one just read
+constexpr int kRangeAhead = kRangeSlots - 2;
 constexpr uint32_t kRangeSlotStride = 144 + 16;      // 128 q bytes + 16 bit-plane bytes (+ pad: spreads the lanes over the banks)
 constexpr uint32_t kRangeWarpBytes = kRangeSlots * 32 * kRangeSlotStride;
 // the rings take 80 KB; the CTA asks for more than half an SM's shared memory so that it has the SM to itself: a warp that
 // shares its scheduler with others of its kind slows down by the round-robin factor
-constexpr size_t kRangeSmem = 120 * 1024;
+constexpr size_t kRangeSmem = kRangeSlots > 4 ? 200 * 1024 : 120 * 1024;
 static_assert(kRangeWarps * kRangeWarpBytes <= kRangeSmem, "k_range rings");
 
 __global__ void __launch_bounds__(32 * kRangeWarps) k_range(const __grid_constant__ EncArgs A, int band, int nframes) {
@@ -1105,17 +1109,18 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range(const __grid_constan
         return tag;
     };
     uint32_t tags[kRangeSlots];                 // tag of the block in each slot (compile-time indexed: the block loop is unrolled by 4)
-    tags[0] = fetch_block(0);
-    tags[1] = fetch_block(1);
-    tags[2] = tags[3] = 0;
+#pragma unroll
+    for (int i = 0; i < kRangeSlots; i++) tags[i] = 0;
+#pragma unroll
+    for (int i = 0; i < kRangeAhead; i++) tags[i] = fetch_block((uint32_t)i);
 
     for (uint32_t b0 = 0; b0 < maxb; b0 += kRangeSlots) {
 #pragma unroll
         for (int k = 0; k < kRangeSlots; k++) {
             // block b0 + k lives in slot k; ask for block b0 + k + 2 (its slot held block b0 + k - 2: read long ago), then wait
             // until at most the two newest requests are pending
-            tags[(k + 2) % kRangeSlots] = fetch_block((uint32_t)((k + 2) % kRangeSlots));
-            cp_async_wait<2>();
+            tags[(k + kRangeAhead) % kRangeSlots] = fetch_block((uint32_t)((k + kRangeAhead) % kRangeSlots));
+            cp_async_wait<kRangeAhead>();
             const uint32_t tag = tags[k];
             const bool have = (tag & 0x80000000u) != 0;
             const uint32_t sl = slot_at((uint32_t)k);
@@ -1387,7 +1392,11 @@ cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s
     const int warps = (n + 31) / 32;
     // one lane per (frame, slice); CTAs of four warps, one per scheduler. The record rings (168 KB) keep a CTA alone on its
     // SM: a warp that shares its scheduler with others of its kind slows down by the round-robin factor.
-    k_range<<<(warps + kRangeWarps - 1) / kRangeWarps, 32 * kRangeWarps, kRangeSmem, s>>>(a, band, nframes);
+    // dynamic shared memory: the rings (80 KB), or more when the caller wants fewer CTAs per SM (a.range_smem)
+    size_t smem = kRangeWarps * kRangeWarpBytes;
+    if ((size_t)a.range_smem > smem) smem = (size_t)a.range_smem;
+    if (smem > kRangeSmem) smem = kRangeSmem;
+    k_range<<<(warps + kRangeWarps - 1) / kRangeWarps, 32 * kRangeWarps, smem, s>>>(a, band, nframes);
     return cudaGetLastError();
 }
 
