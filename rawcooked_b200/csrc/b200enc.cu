@@ -477,7 +477,7 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
         const int p = band % E->kpar;
         if (!serial && emode != 2) CU(cudaStreamWaitEvent(se, E->ev_range[p], 0));
         if (tr) CU(cudaEventRecord(E->trace[band * 6 + 4], se));
-        CU(b200::launch_emit(A[p], n_frames, se));
+        if (!getenv("B200_SKIP_EMIT")) CU(b200::launch_emit(A[p], n_frames, se));     // (experiment knob: timing without the emitter; output invalid)
         if (tr) CU(cudaEventRecord(E->trace[band * 6 + 5], se));
         if (tm) CU(cudaEventRecord(E->tev[band * 4 + 3], s));
         if (!serial) CU(cudaEventRecord(E->ev_emit[p], se));

@@ -1033,6 +1033,10 @@ constexpr int kRangeWarps = 4;                       // one per scheduler
 #endif
 constexpr int kRangeSlots = B200_RANGE_SLOTS;        // blocks in a lane's ring: one being read, kRangeSlots - 2 on their way, one just read
 constexpr int kRangeAhead = kRangeSlots - 2;
+#ifndef B200_RANGE_UNROLL
+#define B200_RANGE_UNROLL 1
+#endif
+constexpr int kRangeUnroll = B200_RANGE_UNROLL;      // 16-record groups of a block unrolled together (the whole kernel unrolled is 100 KB of code)
 constexpr uint32_t kRangeSlotStride = 144 + 16;      // 128 q bytes + 16 bit-plane bytes (+ pad: spreads the lanes over the banks)
 constexpr uint32_t kRangeWarpBytes = kRangeSlots * 32 * kRangeSlotStride;
 // the rings take 80 KB; the CTA asks for more than half an SM's shared memory so that it has the SM to itself: a warp that
@@ -1125,7 +1129,7 @@ __global__ void __launch_bounds__(32 * kRangeWarps) k_range(const __grid_constan
             const bool have = (tag & 0x80000000u) != 0;
             const uint32_t sl = slot_at((uint32_t)k);
             uint2* ck = ((tag >> 30) & 1u ? kC : kY) + (size_t)(tag & 0x3FFFFFFFu) * 2u;
-#pragma unroll
+#pragma unroll(kRangeUnroll)
             for (int gI = 0; gI < 8; gI++) {
                 uint4 q = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);      // no-op records for a lane without a block
                 uint32_t nbits = 0xFFFFFFFFu;
