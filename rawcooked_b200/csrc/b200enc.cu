@@ -281,7 +281,11 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     {
         // Partition: B200_RANGE_SMS SMs (default 24) to k_range, optionally B200_EMIT_SMS to k_emit, the rest to k_model.
         // B200_NO_PARTITION=1 (or a driver without green contexts) falls back to three plain streams on the whole device.
-        int range_sms = 24, emit_sms = 0;
+        // k_range: one lane per (frame, slice), CTAs of 128 lanes, two CTAs per SM (two warps per scheduler cost a fifth of
+        // their speed and halve the SMs taken from k_model); the driver hands out SMs in groups of 8
+        const int range_ctas = (B * ns + 127) / 128;
+        int range_sms = (((range_ctas + 1) / 2) + 7) / 8 * 8, emit_sms = 0;
+        if (range_sms > 32) range_sms = 32;
         if (const char* e = getenv("B200_RANGE_SMS")) range_sms = atoi(e);
         if (const char* e = getenv("B200_EMIT_SMS")) emit_sms = atoi(e);
         E->emit_mode = emit_sms > 0 ? 0 : 1;
@@ -301,8 +305,8 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
                 parted = E->sr && E->sm && (emit_sms == 0 || E->se);
                 if (parted) {
                     A.model_ctas = E->part.sm_count(last);
-                    A.range_smem = 120 * 1024;           // one k_range CTA per SM of its partition
-                    if (const char* e = getenv("B200_RANGE_CTAS_PER_SM")) { int v = atoi(e); if (v >= 2) A.range_smem = 0; }
+                    A.range_smem = 0;                    // the record rings alone (80 KB): two k_range CTAs per SM
+                    if (const char* e = getenv("B200_RANGE_CTAS_PER_SM")) { if (atoi(e) == 1) A.range_smem = 120 * 1024; }
                     A.range_sms = E->part.sm_count(0);
                     for (int pz = 1; pz < E->kpar; pz++) {
                         E->argsN[pz].model_ctas = A.model_ctas; E->argsN[pz].range_smem = A.range_smem; E->argsN[pz].range_sms = A.range_sms;

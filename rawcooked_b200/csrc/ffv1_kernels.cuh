@@ -24,7 +24,7 @@
 namespace b200 {
 
 #ifndef B200_MODEL_THREADS
-#define B200_MODEL_THREADS 512
+#define B200_MODEL_THREADS 768
 #endif
 constexpr int kModelThreads = B200_MODEL_THREADS;   // one CTA per SM when the large context model (162 KB) is in smem
 constexpr int kModelWarps = kModelThreads / 32;
