@@ -145,8 +145,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     if (wmax > 2048) { delete E; return fail(B200_ERR_INVALID, "slice wider than 2048 pixels: use more slices"); }
     // The model kernel keeps the whole context-state table of one plane-set in shared memory; what is left (minus a
     // reserve that lets k_range CTAs run on the same SM) stages the records of one plane-row. Rows whose records do not fit are
-    // coded in up to kMaxSeg column segments. Three layouts of the small tables, tried from the fastest to the leanest:
-    // replicated one_state table + direct first-occurrence table, replicated + hashed, plain + hashed.
+    // coded in up to kMaxSeg column segments.
     int dev_smem = 0;
     cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     const int maxbins = 2 * S.sbits + 1;                        // bins of the largest symbol: 2e+3 with e = sbits-1
@@ -154,28 +153,23 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     const size_t chunk_need = 32 * (size_t)maxbins + b200::kMaxHeaderBins;
     size_t reserve = 0;      // k_range has SMs of its own (SM partition); nothing needs to co-reside with k_model
     if (const char* e = getenv("B200_SMEM_RESERVE")) reserve = (size_t)atoi(e);
-    const int tries[3] = {A.sstride == 32 ? 1 : 0, -1, 0};    // one_state table replicated per bank, or plain
     int best = -1, best_nseg = 0;
     size_t best_cap = 0;
-    // a typical plane-row (one record per bit of the folded residual plus one) should fit the stage in one piece: the replicated
-    // table (8 KB) is given up when it stands in the way of that
-    const size_t typical = (size_t)wmax * (S.sbits + 1) + b200::kMaxHeaderBins;
-    for (int k = 0; k < 3; k++) {
-        if (!tries[k]) continue;
-        const size_t fixed = b200::model_smem_fixed(S.nctx, A.sstride, wmax, 2, tries[k]);
-        if (fixed + reserve + 2 * (chunk_need + 256) > (size_t)dev_smem) continue;
-        size_t capk = (((size_t)dev_smem - reserve - fixed) / 2) & ~(size_t)127;
-        if (capk > row_need) capk = row_need;
-        if (capk > 32640) capk = 32640;             // record offsets inside the stage travel as 16-bit byte offsets (k_model chains)
-        const int nsegk = capk >= row_need ? 1 : (int)(((size_t)wmax * maxbins + (capk - chunk_need) - 1) / (capk - chunk_need));
-        if (capk > best_cap) { best = k; best_nseg = nsegk; best_cap = capk; }
-        if (capk >= typical || capk >= row_need) break;
+    {
+        const size_t fixed = b200::model_smem_fixed(S.nctx, A.sstride, wmax, 2);
+        if (fixed + reserve + 2 * (chunk_need + 256) <= (size_t)dev_smem) {
+            size_t capk = (((size_t)dev_smem - reserve - fixed) / 2) & ~(size_t)127;
+            if (capk > row_need) capk = row_need;
+            if (capk > 32640) capk = 32640;             // record offsets inside the stage travel as 16-bit byte offsets
+            best = 0;
+            best_cap = capk;
+            best_nseg = capk >= row_need ? 1 : (int)(((size_t)wmax * maxbins + (capk - chunk_need) - 1) / (capk - chunk_need));
+        }
     }
     if (best < 0 || best_nseg > b200::kMaxSeg) {
         delete E;
         return fail(B200_ERR_INVALID, "slice too wide for the shared-memory context model: use more slices");
     }
-    A.t1_rep = tries[best];
     A.stage_cap = (int32_t)best_cap;
     A.nseg = best_nseg;
     if (A.band_rows * 3 * A.nseg > 4096) { delete E; return fail(B200_ERR_INVALID, "band too large"); }

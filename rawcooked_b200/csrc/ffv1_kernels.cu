@@ -83,10 +83,10 @@ constexpr uint32_t kNopRec = 0x00FFu;
 //
 // One CTA per (frame, slice, plane-set) and band. Shared memory (dynamic):
 //   states  nctx*sstride B   adaptive state of every (context, slot) of this plane-set (32 B per context, 28 for 8-bit streams)
+//   raw     the payload bytes of the next slice row, as stored in the file (bulk copy); mbar: two mbarriers (states, row)
 //   ring    3 rows x planes x wmax int32   RCT'd samples of rows y, y-1, y-2
 //   qtab    5 x 256 int16    quantisation tables
-//   t1      one_state, indexed by q: either replicated per bank ([64][32] words: lane l reads word (q >> 2) * 32 + l, no
-//           bank conflicts whatever the 32 lanes look up) or a plain 256-byte table when shared memory is short
+//   tpow    one_state iterated 2^i times (runs of zeros); trans: next state by (bit, state)
 //   ent     the samples of the plane-row being coded, grouped by context class (= owner warp), x order inside a class, 16 bytes
 //           each: slots the symbol uses (bit mask), value of the bin of each slot (bit mask), byte offsets of its records in the
 //           stage (2o | (2o + 4e) << 16), folded residual (after the context-sign flip, 18 bits) | context << 18
@@ -102,18 +102,19 @@ constexpr uint32_t kNopRec = 0x00FFu;
 // sample per step with one lane per slot -> S3 records to global memory. Warps never share a context, so there is no
 // barrier inside S2.
 struct ModelSmem {
-    uint8_t* states; int32_t* ring; int16_t* qtab; uint32_t* t1w; uint8_t* t1b;
+    uint8_t* states; uint8_t* raw; uint64_t* mbar; int32_t* ring; int16_t* qtab;
     uint4* ent; uint32_t* ctot; uint16_t* wcnt; uint32_t* segcnt; uint32_t* misc; uint8_t* tpow; uint8_t* trans; uint16_t* stage;
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+// the bytes of one slice row of the payload, widened to 16-byte boundaries at both ends (6 bytes per pixel at most)
+__host__ __device__ inline size_t model_raw_cap(int wmax) { return align16((size_t)wmax * 6 + 48); }
 
-// bytes of everything except the record staging area. t1_rep > 0: one_state table replicated per bank, else a plain table.
-size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int t1_rep) {
-    const bool rep = t1_rep > 0;
+// bytes of everything except the record staging area
+size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes) {
     size_t n = align16((size_t)nctx * sstride);
+    n += model_raw_cap(wmax) + 16;           // raw payload row + two mbarriers
     n += align16((size_t)3 * planes * wmax * 4);
     n += 5 * 256 * 2;
-    n += rep ? 64 * 32 * 4 : 256;
     n += (size_t)wmax * 16;                  // ent
     const int nch = (wmax + 31) / 32;
     n += align16((size_t)nch * 4);           // ctot
@@ -124,17 +125,17 @@ size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int t1_rep)
     n += 512;                                // trans
     return n;
 }
-size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int t1_rep, int stage_cap) {
-    return model_smem_fixed(nctx, sstride, wmax, planes, t1_rep) + align16((size_t)stage_cap * 2);
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int stage_cap) {
+    return model_smem_fixed(nctx, sstride, wmax, planes) + align16((size_t)stage_cap * 2);
 }
 
-__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes, int t1_rep) {
-    const bool rep = t1_rep > 0;
+__device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride, int wmax, int planes) {
     ModelSmem m;
     m.states = base; base += align16((size_t)nctx * sstride);
+    m.raw = base; base += model_raw_cap(wmax);
+    m.mbar = reinterpret_cast<uint64_t*>(base); base += 16;
     m.ring = reinterpret_cast<int32_t*>(base); base += align16((size_t)3 * planes * wmax * 4);
     m.qtab = reinterpret_cast<int16_t*>(base); base += 5 * 256 * 2;
-    m.t1w = reinterpret_cast<uint32_t*>(base); m.t1b = base; base += rep ? 64 * 32 * 4 : 256;
     m.ent = reinterpret_cast<uint4*>(base); base += (size_t)wmax * 16;
     const int nch = (wmax + 31) / 32;
     m.ctot = reinterpret_cast<uint32_t*>(base); base += align16((size_t)nch * 4);
@@ -147,22 +148,6 @@ __device__ __forceinline__ ModelSmem carve(uint8_t* base, int nctx, int sstride,
     return m;
 }
 
-constexpr int kMaxPixPerThread = 2048 / kModelThreads;      // wmax <= 2048
-#ifndef B200_DENSE_MIN
-#define B200_DENSE_MIN 3      // measured on B200: 1 -> 219 ms, 3 -> 202, 5 -> 210, 7 -> 226, 10 -> 247, 16 -> 287 per 64 4K frames
-#endif
-constexpr int kDenseMin = B200_DENSE_MIN;        // rounds with fewer samples than this run one sample per step (one lane per slot)
-#ifndef B200_CHAIN_MIN
-#define B200_CHAIN_MIN 3       // measured on B200 (ms per 64 grainy 4K frames): 2 -> 192, 3 -> 193, 5 -> 199, 8 -> 205; low-noise content is indifferent
-#endif
-constexpr int kChainMin = B200_CHAIN_MIN;      // a context with at least this many samples in a batch is coded as a chain
-#ifndef B200_SERIAL_S2
-#define B200_SERIAL_S2 1        // 1: the class warps code their samples one after the other, one lane per slot; 0: batches of 32 (zero runs, chains, rank rounds)
-#endif
-#ifndef B200_CHAIN_SCAN
-#define B200_CHAIN_SCAN 12
-#endif
-constexpr int kChainScan = B200_CHAIN_SCAN;    // chains of at least this many samples walk the whole batch instead of searching for their members
 
 // -DB200_PHASE_TIMING: thread 0 of every CTA accumulates the cycles between phase boundaries into flags[16 + 2*phase]
 #ifdef B200_PHASE_TIMING
@@ -189,31 +174,32 @@ __device__ __forceinline__ uint32_t lds_u8_volatile(uint32_t a) { uint32_t v; as
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-template <bool kRep>
-struct T1 {             // one_state lookup by q = sp - 1 (the table never changes after the kernel's prologue)
-    uint32_t base;          // shared address; replicated: + lane * 4 already applied
-    __device__ __forceinline__ uint32_t operator()(uint32_t q) const {
-        if (kRep) return __byte_perm(lds_u32(base + ((q & 0xFCu) << 5)), 0, (q & 3u) | 0x4440u);
-        return lds_u8(base + q);
-    }
-};
 
-// One bin on the register-resident state row: slot SLOT of the context. The state is read from S0 (the row as loaded,
-// or the running row for the two slots a symbol can use more than once), `used` lanes put the new state into S and write
-// the record to shared address dst (the other lanes write to `dummy`). Branch-free.
-template <bool kCompact, int SLOT, class TT>
-__device__ __forceinline__ void slot_step(const uint32_t (&S0)[8], uint32_t (&S)[8], bool used, bool bit, uint32_t dst, uint32_t dummy, const TT& t1) {
-    constexpr int ci = cslot<kCompact>(SLOT), wi = ci >> 2, bi = ci & 3;
-    const uint32_t st = __byte_perm(S0[wi], 0, 0x4440 | bi);
-    const int s1 = bit ? 1 : -1;
-    const uint32_t rec = (uint32_t)((int)st * s1 + 255);            // q | bit << 8
-    const uint32_t n = t1(rec & 255u);                              // one_state[sp]
-    const uint32_t nx = (uint32_t)((int)n * s1 + (bit ? 0 : 256));  // bit ? one_state[st] : zero_state[st] = 256 - one_state[256 - st]
-    const uint32_t ins = __byte_perm(S[wi], nx, bi == 0 ? 0x3214 : bi == 1 ? 0x3240 : bi == 2 ? 0x3410 : 0x4210);
-    S[wi] = used ? ins : S[wi];
-    sts_u16(used ? dst : dummy, rec);
+// ---- bulk asynchronous copies (the 1-D form of TMA, UBLKCP in SASS) and the mbarrier they report to: the context-state table
+// of an item (162 KB) comes in and goes out as one copy each, the payload row of the next slice row is in flight while this one
+// is coded; no thread spends issue slots on either
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
-
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // A symbol with exponent > 9 on the one-lane-per-slot path: slots 10 and 31 take several bins of the symbol; lane s runs the bins
 // of its slot on the state it holds and returns the new state (rangecoder::s, FFV1_RangeCoder.cpp:135-171). Rare (|residual| >=
@@ -244,8 +230,8 @@ __device__ __noinline__ uint32_t wide_symbol(const uint4 E, uint32_t st, int lan
     return st;
 }
 
-template <bool kCompact, bool kRep>
-__device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t* smem_raw, int slice, int ps, int frame) {
+template <bool kCompact>
+__device__ __forceinline__ void k_model_body(const EncArgs& A, int band, int nframes, uint8_t* smem_raw, int slice, int ps, int frame, uint32_t& ph_state, uint32_t& ph_row) {
     const SliceGeom g = A.geom[slice];
     const int r0 = band * A.band_rows;
     if (r0 >= g.h) return;
@@ -255,52 +241,65 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kModelThreads / 32;
     constexpr int kRow = kCompact ? 28 : 32;                   // state bytes per context
-    constexpr int kWords = kCompact ? 7 : 8;
-    const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, planes, A.t1_rep);
+    const ModelSmem S = carve(smem_raw, A.nctx, kRow, wmax, 2);      // one layout for both plane-sets: the constant tables are loaded once
     const uint32_t stage_cap = (uint32_t)A.stage_cap;
-    T1<kRep> t1;
-    t1.base = smem_addr(S.t1b) + (kRep ? lane * 4 : 0);
-    const uint32_t dummy = smem_addr(S.misc) + warp * 64 + lane * 2;   // where the lanes that have no bin in a step put their record
     const uint32_t stage_a = smem_addr(S.stage), states_a = smem_addr(S.states), tpow_a = smem_addr(S.tpow), trans_a = smem_addr(S.trans);
     const uint32_t lt = (1u << lane) - 1u;
 
     const size_t fs = (size_t)frame * A.nslices + slice;
     const int state_bytes = (int)align16((size_t)A.nctx * kRow);
     uint8_t* save = A.state_save + (fs * 2 + ps) * (size_t)state_bytes;
-    {   // context states: 128 at the start of every frame (intra-only), else carried from the previous band
+    const uint32_t mb_state = smem_addr(S.mbar), mb_row = mb_state + 8u, raw_a = smem_addr(S.raw);
+    // context states: 128 at the start of every frame (intra-only), else carried from the previous band: one bulk copy, waited
+    // for after the first rows have been loaded (the constant tables were loaded once by k_model_loop)
+    if (band == 0) {
         const int n16 = state_bytes >> 4;
         uint4* d = reinterpret_cast<uint4*>(S.states);
-        if (band == 0) {
-            const uint4 v = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-            for (int i = tid; i < n16; i += kModelThreads) d[i] = v;
-        } else {
-            const uint4* s = reinterpret_cast<const uint4*>(save);
-            for (int i = tid; i < n16; i += kModelThreads) d[i] = s[i];
-        }
-        for (int i = tid; i < 5 * 256; i += kModelThreads) S.qtab[i] = A.qtab[i];
-        if (kRep) {
-            for (int i = tid; i < 64 * 32; i += kModelThreads) S.t1w[i] = reinterpret_cast<const uint32_t*>(A.t1q)[i >> 5];
-        } else {
-            for (int i = tid; i < 256; i += kModelThreads) S.t1b[i] = A.t1q[i];
-        }
-        for (int i = tid; i < 5 * 256; i += kModelThreads) S.tpow[i] = A.tpow[i];
-        // next state by (bit, state): the chains' only dependency from sample to sample is one look-up in this table
-        for (int i = tid; i < 512; i += kModelThreads) {
-            const int st = i & 255;
-            S.trans[i] = st == 0 ? (uint8_t)0 : (i >> 8) ? A.t1q[st - 1] : (uint8_t)(256 - A.t1q[255 - st]);
-        }
+        const uint4 v = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        for (int i = tid; i < n16; i += kModelThreads) d[i] = v;
+    } else if (tid == 0) {
+        mbar_expect_tx(mb_state, (uint32_t)state_bytes);
+        bulk_g2s(states_a, save, (uint32_t)state_bytes, mb_state);
     }
     const uint8_t* fin = A.in + (size_t)frame * A.frame_bytes;
     const int off = 1 << A.bits;
 
-    // forward RCT of pixel x of slice row y (inverse of Transform.cpp:29-37); p0 = Y or Cb, p1 = Cr
-    auto fetch = [&](int y, int x, int& p0, int& p1) {
-        const uint8_t* row = fin + (size_t)(g.y0 + y) * A.row_bytes;
+    // forward RCT of pixel x of a slice row whose payload row starts at `row` (inverse of Transform.cpp:29-37); p0 = Y or Cb, p1 = Cr
+    auto fetch_from = [&](const uint8_t* row, int x, int& p0, int& p1) {
         int r, gg, b;
         load_rgb(row, A.layout, g.x0 + x, r, gg, b);
         if (A.swap_bg) { int t = gg; gg = b; b = t; }
         b -= gg; r -= gg; gg += (b + r) >> 2; b += off; r += off;
         if (ps == 0) { p0 = gg; p1 = 0; } else { p0 = b; p1 = r; }
+    };
+    auto fetch = [&](int y, int x, int& p0, int& p1) { fetch_from(fin + (size_t)(g.y0 + y) * A.row_bytes, x, p0, p1); };
+    // the bytes of a payload row this slice reads: [first_off, end_off) from the start of the row
+    uint32_t first_off, end_off;
+    {
+        const uint32_t x0 = (uint32_t)g.x0, x1 = (uint32_t)(g.x0 + w);
+        switch (A.layout) {
+            case B200_DPX_RGB_8: case B200_TIFF_RGB_8: first_off = 3u * x0; end_off = 3u * x1; break;
+            case B200_DPX_RGB_10_FILLED_A_LE: case B200_DPX_RGB_10_FILLED_A_BE: first_off = 4u * x0; end_off = 4u * x1; break;
+            case B200_DPX_RGB_12_PACKED_BE: first_off = ((36u * x0) >> 5) * 4u; end_off = (((36u * x1 - 1u) >> 5) + 1u) * 4u; break;
+            default: first_off = 6u * x0; end_off = 6u * x1; break;
+        }
+        if (end_off > A.row_bytes) end_off = A.row_bytes;
+    }
+    const uintptr_t in_end = (reinterpret_cast<uintptr_t>(A.in) + (size_t)nframes * A.frame_bytes) & ~(uintptr_t)15;
+    // slice row y as a bulk copy: the 16-byte aligned window around its bytes (none when the window would pass the end of the input)
+    auto row_window = [&](int y, uintptr_t& wlo, uint32_t& len) -> bool {
+        const uintptr_t R = reinterpret_cast<uintptr_t>(fin + (size_t)(g.y0 + y) * A.row_bytes);
+        wlo = (R + first_off) & ~(uintptr_t)15;
+        const uintptr_t whi = (R + end_off + 15) & ~(uintptr_t)15;
+        len = (uint32_t)(whi - wlo);
+        return whi <= in_end;
+    };
+    auto issue_row = [&](int y) {          // one thread
+        uintptr_t wlo; uint32_t len;
+        if (row_window(y, wlo, len)) {
+            mbar_expect_tx(mb_row, len);
+            bulk_g2s(raw_a, reinterpret_cast<const void*>(wlo), len, mb_row);
+        }
     };
     // rows above the slice are zero (FFV1_Slice.cpp:409-410 memset)
     auto load_row = [&](int y) {
@@ -330,6 +329,8 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
         for (int i = tid; i < nh; i += kModelThreads) S.stage[i] = A.hdr_bins[(size_t)slice * kMaxHeaderBins + i];
         seg_extra = (uint32_t)nh;
     }
+    if (tid == 0 && r0 + 1 < r1) issue_row(r0 + 1);
+    if (band != 0) { mbar_wait(mb_state, ph_state); ph_state ^= 1u; }
     __syncthreads();
 
     const int nchunk = (w + 31) >> 5;
@@ -339,7 +340,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
     //   lane 0 zero flag | 1..10 exponent i = lane-1 (slot 10 also takes i > 9) | 11..21 sign for e = lane-11 |
     //   22..31 mantissa bit i = lane-22 (slot 31 also takes i > 9)
     const bool isB = lane >= 1 && lane <= 10, isD = lane >= 11 && lane <= 21;
-    const int li = isB ? lane - 1 : isD ? lane - 11 : lane - 22;
     const bool lane_has_slot = !kCompact || !(lane == 10 || lane == 20 || lane == 21 || lane >= 30);
     const int lslot = cslot<kCompact>(lane);
     unsigned long long bins_total = 0;
@@ -348,17 +348,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
 #endif
 
     for (int y = r0; y < r1; y++) {
-        // software prefetch of the next payload row into registers; it lands in the ring once the last plane of this
-        // row has read its neighbours
-        int nx0[kMaxPixPerThread], nx1[kMaxPixPerThread];
         const bool have_next = y + 1 < r1;
-        if (have_next) {
-#pragma unroll
-            for (int k = 0; k < kMaxPixPerThread; k++) {
-                const int x = tid + k * kModelThreads;
-                if (x < w) fetch(y + 1, x, nx0[k], nx1[k]);
-            }
-        }
         for (int pl = 0; pl < planes; pl++) {
             const int32_t* cur = S.ring + ((size_t)((y + 3) % 3) * planes + pl) * wmax;
             const int32_t* prv = S.ring + ((size_t)((y + 2) % 3) * planes + pl) * wmax;
@@ -416,14 +406,27 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
             }
             __syncthreads();
             PHASE_MARK(0);
-            // the next payload row may now replace row y-2 (nobody reads it any more)
+            // the next payload row (in flight since the previous row, or since the prologue) may now replace row y-2 in the ring
+            // (nobody reads that one any more)
+            bool row_taken = false;
             if (have_next && pl == planes - 1) {
                 int32_t* dst = S.ring + (size_t)((y + 4) % 3) * planes * wmax;
-#pragma unroll
-                for (int k = 0; k < kMaxPixPerThread; k++) {
-                    const int x = tid + k * kModelThreads;
-                    if (x < w) { dst[x] = nx0[k]; if (ps) dst[wmax + x] = nx1[k]; }
+                uintptr_t wlo; uint32_t len;
+                const uint8_t* rowp;
+                if (row_window(y + 1, wlo, len)) {
+                    mbar_wait(mb_row, ph_row);
+                    ph_row ^= 1u;
+                    rowp = S.raw + (ptrdiff_t)(reinterpret_cast<uintptr_t>(fin + (size_t)(g.y0 + y + 1) * A.row_bytes) - wlo);
+                } else {
+                    rowp = fin + (size_t)(g.y0 + y + 1) * A.row_bytes;
                 }
+                for (int x = tid; x < w; x += kModelThreads) {
+                    int p0, p1;
+                    fetch_from(rowp, x, p0, p1);
+                    dst[x] = p0;
+                    if (ps) dst[wmax + x] = p1;
+                }
+                row_taken = true;
             }
             // exclusive prefix of the chunk totals, every warp for itself: lane l holds chunks l and l + 32
             uint32_t ex0, ex1, total;
@@ -522,6 +525,7 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 }
             }
             __syncthreads();
+            if (row_taken && tid == 0 && y + 2 < r1) issue_row(y + 2);      // the raw row has been consumed by everybody
             uint32_t kcur = klo;             // next sample of my class (the cursor runs on over the column segments)
             const uint32_t rc_base = ((uint32_t)(fs * A.band_rows + (y - r0)) * 3u + (uint32_t)(ps ? 1 + pl : 0)) * (uint32_t)A.nseg;
             for (int s = 0; s < nsg; s++) {
@@ -532,7 +536,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                 // ---- S2 (K3): warp q = context class q. Its samples of this segment, in x order, 32 per batch.
                 {
                     const uint32_t kend = nsg == 1 ? khi : kcur + S.segcnt[s * NW + warp];
-#if B200_SERIAL_S2
                     // The samples of my class go one after the other, in list (= bitstream) order; lane s holds the state of slot s of
                     // the context being coded. What a symbol does to the 32 slots comes as the two masks S1 left in its entry (slot
                     // used / bin value), read from shared memory two samples ahead (same address for every lane); lanes whose slot
@@ -616,254 +619,6 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
                         flush();
                         __syncwarp();
                     }
-#else
-                    for (;;) {
-                        const uint32_t idx = kcur + (uint32_t)lane;
-                        const bool have = idx < kend;
-                        const uint32_t hmask = __ballot_sync(0xffffffffu, have);
-                        if (!hmask) break;
-                        uint4 en = make_uint4(1u, 1u, 0u, 0u);
-                        if (have) en = S.ent[idx];
-                        const int v = ((int)(en.w << 14)) >> 14;
-                        const uint32_t cx = have ? (en.w >> 18) : 0x10000u + (uint32_t)lane;
-                        const uint32_t o = (en.z & 0xFFFFu) >> 1;
-                        // rounds: samples of the batch that share a context go one after the other
-                        const uint32_t mm = __match_any_sync(0xffffffffu, cx);
-                        const int rank = __popc(mm & lt);
-                        // runs of zeros: when every sample of the batch that uses a context has residual 0 (flat areas, mattes,
-                        // black frames), the k-th of them sees state one_state^k(st) of slot 0 and nothing else moves: all of
-                        // them at once, through the tables of one_state^(2^i)
-                        bool have2 = have;
-                        const bool z = have && v == 0;
-                        if (__any_sync(0xffffffffu, z)) {
-                            const uint32_t mz = __match_any_sync(0xffffffffu, z ? cx : 0x40000u + (uint32_t)lane);
-                            const bool pure = z && mz == mm;
-                            if (__any_sync(0xffffffffu, pure)) {
-                                const uint32_t sa = states_a + (cx & 0xFFFFu) * (uint32_t)kRow;      // slot 0 = byte 0 of the row
-                                uint32_t st = 0;
-                                if (pure) st = lds_u8_volatile(sa);
-                                __syncwarp();
-                                if (pure) {
-                                    const int j = __popc(mz & lt);
-#pragma unroll
-                                    for (int kk = 0; kk < 5; kk++)
-                                        if ((j >> kk) & 1) st = lds_u8(tpow_a + kk * 256 + st);
-                                    sts_u16(stage_a + o * 2u, st + 255u);                             // q = st - 1, bit 1
-                                    if (j == __popc(mz) - 1) sts_u8(sa, lds_u8(tpow_a + st));
-                                }
-                                __syncwarp();
-                                have2 = have && !pure;
-                            }
-                        }
-                        const bool nz = v != 0;
-                        const uint32_t a = (uint32_t)abs(v);
-                        const int e = nz ? 31 - __clz(a) : -1;
-                        const bool neg = v < 0;
-                        // ---- chains: a context used by kChainMin or more samples of the batch (low-noise and flat content: a
-                        // handful of contexts take most of a row) is coded as one chain: lane s keeps the state of slot s in a
-                        // register from the first to the last sample; what a sample does to the 32 slots comes as two masks
-                        // (slot used / bin value) its own lane has prepared, so a step is a dozen instructions and the only
-                        // dependency from sample to sample is one table look-up. Symbols with exponent > 9 (two slots used more
-                        // than once) keep to the rounds below.
-                        {
-                            const int gsz = __popc(mm);
-                            const bool big = have2 && gsz >= kChainMin;
-                            const uint32_t bigm = __ballot_sync(0xffffffffu, big);
-                            const uint32_t wide = __ballot_sync(0xffffffffu, big && e > 9);
-                            if (bigm) {
-                                // a group is chained only if none of its members has e > 9
-                                const bool chain = big && (mm & wide) == 0;
-                                // record index of my slot's bin inside a symbol of exponent e: kA + kE * e with kE = 0 (zero flag,
-                                // exponent) or 2 (sign, mantissa): a sample's entry holds both byte offsets, 2o and 2o + 4e, in one word.
-                                // Lane constants of the sample loop, pinned in registers (the compiler would otherwise rebuild them from
-                                // the lane number in every iteration): stage address of my bin, which half of the offset word I take, my
-                                // slot's bit, the two halves of the (bit, state) table
-                                const int kA = lane == 0 ? 0 : isB ? lane : isD ? 2 : 23 - lane;
-                                uint32_t abase = stage_a + 2u * (uint32_t)kA, hsel = (lane == 0 || isB) ? 0x4410u : 0x4432u, lbit = 1u << lane;
-                                uint32_t tr0 = trans_a, tr1 = trans_a + 256u;
-                                asm volatile("" : "+r"(abase), "+r"(hsel), "+r"(lbit), "+r"(tr0), "+r"(tr1));
-                                const uint32_t eb = smem_addr(S.ent) + kcur * 16u;            // the batch's entries, lane order
-                                // one sample of the chain: its entry (slots used, bin values, record offsets) was read from shared
-                                // memory (same address for every lane) two samples earlier; lanes whose slot the symbol does not use keep
-                                // their state (predicated, not branched), so the only latency from sample to sample is the (bit, state)
-                                // look-up of the slots in use
-                                auto chain_step = [&](const uint4& E, uint32_t& st) {
-                                    const uint32_t used = E.x & lbit, bitm = E.y & lbit;
-                                    const uint32_t rec = bitm ? 255u + st : 255u - st;
-                                    const uint32_t dst = abase + __byte_perm(E.z, 0, hsel);
-                                    const uint32_t ta = (bitm ? tr1 : tr0) + st;
-                                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.u16 [%1], %2;\n\t@p ld.shared.u8 %0, [%4];\n\t}"
-                                                 : "+r"(st) : "r"(dst), "h"((uint16_t)rec), "r"(used), "r"(ta) : "memory");
-                                };
-                                uint32_t leaders = __ballot_sync(0xffffffffu, chain && rank == 0);
-                                while (leaders) {
-                                    const int L = __ffs(leaders) - 1;
-                                    leaders &= leaders - 1;
-                                    uint32_t members = __shfl_sync(0xffffffffu, mm, L);
-                                    const uint32_t cj = __shfl_sync(0xffffffffu, cx, L);
-                                    const uint32_t sp = states_a + cj * (uint32_t)kRow + (uint32_t)lslot;
-                                    uint32_t st = lane_has_slot ? lds_u8_volatile(sp) : 128u;
-                                    int n = __popc(members);
-                                    if (n >= kChainScan) {
-                                        // a long chain (a hot context takes most of the batch): walk all 32 entries of the batch in order,
-                                        // entry j + 2 on its way while entry j is coded, and skip the ones of other contexts with a
-                                        // warp-uniform test: no bit search, no address arithmetic, nothing but the look-up in the way
-                                        uint4 E0 = lds_v4(eb), E1 = lds_v4(eb + 16u);
-#pragma unroll
-                                        for (int jj = 0; jj < 32; jj += 2) {
-                                            const uint4 F0 = E0, F1 = E1;
-                                            if (jj + 2 < 32) E0 = lds_v4(eb + (uint32_t)(jj + 2) * 16u);
-                                            if (jj + 3 < 32) E1 = lds_v4(eb + (uint32_t)(jj + 3) * 16u);
-                                            if (members & (1u << jj)) chain_step(F0, st);
-                                            if (members & (2u << jj)) chain_step(F1, st);
-                                        }
-                                        if (lane_has_slot) sts_u8(sp, st);
-                                        continue;
-                                    }
-                                    int j = 0;
-                                    auto next_entry = [&]() -> uint4 {       // entry of the next member (the last one again once they are used up)
-                                        if (members) { j = __ffs(members) - 1; members &= members - 1; }
-                                        return lds_v4(eb + (uint32_t)j * 16u);
-                                    };
-                                    uint4 EA = next_entry(), EB = next_entry();
-                                    for (;;) {
-                                        chain_step(EA, st);
-                                        EA = next_entry();
-                                        if (--n == 0) break;
-                                        chain_step(EB, st);
-                                        EB = next_entry();
-                                        if (--n == 0) break;
-                                    }
-                                    if (lane_has_slot) sts_u8(sp, st);
-                                }
-                                __syncwarp();
-                                have2 = have2 && !chain;
-                            }
-                        }
-                        const int maxr = __reduce_max_sync(0xffffffffu, have2 ? rank : 0);
-                        for (int rr = 0; rr <= maxr; rr++) {
-                            const bool act = have2 && rank == rr;
-                            const uint32_t am = __ballot_sync(0xffffffffu, act);
-                            if (__popc(am) >= kDenseMin) {
-                                // ---- one lane per sample, state row in registers
-                                const int emax = __reduce_max_sync(0xffffffffu, act ? e : -1);
-                                const int emin = __reduce_min_sync(0xffffffffu, (act && nz) ? e : 99);
-                                const bool wnz = act && nz;
-                                const uint32_t pL = stage_a + o * 2u;
-                                const uint32_t pR = pL + (uint32_t)(2 * e + 2) * 2u;
-                                uint32_t R[8], R0[8];
-                                uint8_t* row = S.states + (size_t)(cx & 0xFFFFu) * kRow;
-                                if (act) {
-                                    if (!kCompact) {
-                                        const uint4 w0 = reinterpret_cast<const uint4*>(row)[0], w1 = reinterpret_cast<const uint4*>(row)[1];
-                                        R[0] = w0.x; R[1] = w0.y; R[2] = w0.z; R[3] = w0.w; R[4] = w1.x; R[5] = w1.y; R[6] = w1.z; R[7] = w1.w;
-                                    } else {
-#pragma unroll
-                                        for (int i = 0; i < kWords; i++) R[i] = reinterpret_cast<const uint32_t*>(row)[i];
-                                        R[7] = 0;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 8; i++) R[i] = 0x80808080u;
-                                }
-#pragma unroll
-                                for (int i = 0; i < 8; i++) R0[i] = R[i];
-                                slot_step<kCompact, 0>(R0, R, act, !nz, pL, dummy, t1);
-                                // exponent, unary: bins 1 + i, i = 0..e (1 while i < e)
-                                // (warp-uniform skips only in coarse groups: the steps inside a group are independent and overlap)
-#define EXP_STEP(i) slot_step<kCompact, 1 + (i)>(R0, R, wnz && (i) <= e, (i) < e, pL + 2 * (1 + (i)), dummy, t1);
-                                if (emax >= 0) { EXP_STEP(0) EXP_STEP(1) EXP_STEP(2) EXP_STEP(3) }
-                                if (emax >= 4) { EXP_STEP(4) EXP_STEP(5) EXP_STEP(6) EXP_STEP(7) EXP_STEP(8) }
-#undef EXP_STEP
-                                if (!kCompact) {
-                                    for (int i = 9; i <= emax; i++) slot_step<kCompact, 10>(R, R, wnz && i <= e, i < e, pL + 2 * (1 + i), dummy, t1);
-                                }
-                                // sign: bin 2e + 2, slot 11 + min(e, 10)
-#define SGN_STEP(j) slot_step<kCompact, 11 + (j)>(R0, R, wnz && e == (j), neg, pR, dummy, t1);
-                                if (emin <= 4 && emax >= 0) { SGN_STEP(0) SGN_STEP(1) SGN_STEP(2) SGN_STEP(3) SGN_STEP(4) }
-                                if (emin <= 8 && emax >= 5) { SGN_STEP(5) SGN_STEP(6) SGN_STEP(7) SGN_STEP(8) }
-                                if (!kCompact) {
-                                    if (emax >= 9) { SGN_STEP(9) }
-                                    if (emax >= 10) slot_step<kCompact, 21>(R0, R, wnz && e >= 10, neg, pR, dummy, t1);
-                                }
-#undef SGN_STEP
-                                // mantissa, from the top bit down: bit i is bin 2e + 1 - i, slot 22 + min(i, 9)
-                                if (!kCompact) {
-                                    for (int i = emax - 1; i >= 9; i--) slot_step<kCompact, 31>(R, R, wnz && i < e, (a >> i) & 1u, pR - 2 * (1 + i), dummy, t1);
-                                }
-#define MAN_STEP(i) slot_step<kCompact, 22 + (i)>(R0, R, wnz && (i) < e, (a >> (i)) & 1u, pR - 2 * (1 + (i)), dummy, t1);
-                                if (emax >= 5) {
-                                    if (!kCompact) { MAN_STEP(8) }
-                                    MAN_STEP(7) MAN_STEP(6) MAN_STEP(5) MAN_STEP(4)
-                                }
-                                if (emax >= 1) { MAN_STEP(3) MAN_STEP(2) MAN_STEP(1) MAN_STEP(0) }
-#undef MAN_STEP
-                                if (act) {
-                                    if (!kCompact) {
-                                        reinterpret_cast<uint4*>(row)[0] = make_uint4(R[0], R[1], R[2], R[3]);
-                                        reinterpret_cast<uint4*>(row)[1] = make_uint4(R[4], R[5], R[6], R[7]);
-                                    } else {
-#pragma unroll
-                                        for (int i = 0; i < kWords; i++) reinterpret_cast<uint32_t*>(row)[i] = R[i];
-                                    }
-                                }
-                            } else {
-                                // ---- a few samples: one per step, lane s = slot s of the context (slots are independent chains)
-                                uint32_t todo = am;
-                                while (todo) {
-                                    const int j = __ffs(todo) - 1;
-                                    todo &= todo - 1;
-                                    const int vj = __shfl_sync(0xffffffffu, v, j);                 // warp-uniform
-                                    const uint32_t cj = __shfl_sync(0xffffffffu, cx, j);
-                                    const uint32_t ob = __shfl_sync(0xffffffffu, o, j);
-                                    const uint32_t aj = (uint32_t)abs(vj);
-                                    const int ej = 31 - __clz(aj | 1);
-                                    const uint32_t sp = states_a + cj * (uint32_t)kRow + (uint32_t)lslot;
-                                    if (ej <= 9) {     // every lane has at most one bin
-                                        const bool nzj = vj != 0;
-                                        const bool has = lane_has_slot && (lane == 0 ? true : (nzj && (isB ? li <= ej : isD ? li == ej : li < ej)));
-                                        const bool bit = lane == 0 ? !nzj : isB ? (li < ej) : isD ? (vj < 0) : (((aj >> li) & 1u) != 0);
-                                        const int idx = lane == 0 ? 0 : isB ? 1 + li : isD ? 2 * ej + 2 : 2 * ej + 1 - li;
-                                        if (has) {
-                                            const uint32_t st = lds_u8_volatile(sp);
-                                            const int s1 = bit ? 1 : -1;
-                                            const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                            sts_u16(stage_a + (ob + (uint32_t)idx) * 2u, rec);
-                                            sts_u8(sp, (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256)));
-                                        }
-                                    } else {
-                                        int n2 = 0, i0b = 0, step = 0;     // n2 bins; bin k uses index i = i0b + k*step
-                                        if (lane == 0) n2 = 1;
-                                        else if (lane <= 9) { n2 = 1; i0b = lane - 1; }
-                                        else if (lane == 10) { n2 = ej - 8; i0b = 9; step = 1; }
-                                        else if (lane <= 21) { n2 = (lane - 11) == min(ej, 10); }
-                                        else if (lane <= 30) { n2 = 1; i0b = lane - 22; }
-                                        else { n2 = ej - 9; i0b = ej - 1; step = -1; }
-                                        if (n2) {
-                                            uint32_t st = lds_u8_volatile(sp);
-                                            for (int kk = 0; kk < n2; kk++) {
-                                                const int i = i0b + kk * step;
-                                                bool bit; uint32_t idx;
-                                                if (lane == 0) { bit = false; idx = 0; }
-                                                else if (lane <= 10) { bit = i < ej; idx = 1 + i; }
-                                                else if (lane <= 21) { bit = vj < 0; idx = 2 * ej + 2; }
-                                                else { bit = ((aj >> i) & 1u) != 0; idx = 2 * ej + 1 - i; }
-                                                const int s1 = bit ? 1 : -1;
-                                                const uint32_t rec = (uint32_t)((int)st * s1 + 255);
-                                                sts_u16(stage_a + (ob + idx) * 2u, rec);
-                                                st = (uint32_t)((int)t1(rec & 255u) * s1 + (bit ? 0 : 256));
-                                            }
-                                            sts_u8(sp, st);
-                                        }
-                                    }
-                                }
-                            }
-                            __syncwarp();       // the next round / batch reads the state rows this one wrote
-                        }
-                        kcur += (uint32_t)__popc(hmask);
-                        if (hmask != 0xffffffffu) break;
-                    }
-#endif
                 }
                 // no-op records up to the next whole block
                 const uint32_t padded = (seg_total + (uint32_t)kBlockRecs - 1u) & ~((uint32_t)kBlockRecs - 1u);
@@ -910,42 +665,57 @@ __device__ __forceinline__ void k_model_body(const EncArgs& A, int band, uint8_t
 #endif
     if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(A.flags + 2), bins_total);
     __syncthreads();
-    if (r1 < g.h) {   // carry the states to the next band
-        const int n16 = state_bytes >> 4;
-        const uint4* s = reinterpret_cast<const uint4*>(S.states);
-        uint4* d = reinterpret_cast<uint4*>(save);
-        for (int i = tid; i < n16; i += kModelThreads) d[i] = s[i];
+    if (r1 < g.h) {   // carry the states to the next band: one bulk copy out of shared memory (its completion is awaited by
+                      // k_model_loop before the table is touched again)
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) bulk_s2g(save, states_a, (uint32_t)state_bytes);
     }
 }
 
 // Persistent grid: every CTA pulls (frame, slice, plane-set) items from a counter until none is left, the Cb/Cr items (twice
 // the work) first. The grid is the number of SMs minus the ones left to k_range and k_emit, which must never wait behind
 // queued model CTAs (launch_model).
-template <bool kCompact, bool kRep>
+template <bool kCompact>
 __device__ __forceinline__ void k_model_loop(const EncArgs& A, int band, int nframes, uint8_t* smem_raw) {
     __shared__ int s_item;
     const int nfs = nframes * A.nslices, nitems = nfs * 2;
+    const int tid = threadIdx.x;
+    {   // what every item needs, once per CTA: the quantisation tables, the zero-run and (bit, state) tables, the mbarriers
+        const ModelSmem S = carve(smem_raw, A.nctx, kCompact ? 28 : 32, A.wmax, 2);
+        for (int i = tid; i < 5 * 256; i += kModelThreads) S.qtab[i] = A.qtab[i];
+        for (int i = tid; i < 5 * 256; i += kModelThreads) S.tpow[i] = A.tpow[i];
+        // next state by (bit, state): the only dependency from sample to sample of a context is one look-up in this table
+        for (int i = tid; i < 512; i += kModelThreads) {
+            const int st = i & 255;
+            S.trans[i] = st == 0 ? (uint8_t)0 : (i >> 8) ? A.t1q[st - 1] : (uint8_t)(256 - A.t1q[255 - st]);
+        }
+        if (tid == 0) {
+            mbar_init(smem_addr(S.mbar), 1);
+            mbar_init(smem_addr(S.mbar) + 8u, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    uint32_t ph_state = 0, ph_row = 0;
     for (;;) {
+        if (tid == 0) bulk_wait_read();        // the state table of the previous item has left shared memory
         __syncthreads();
-        if (threadIdx.x == 0) s_item = (int)atomicAdd(A.work_ctr + band, 1u);
+        if (tid == 0) s_item = (int)atomicAdd(A.work_ctr + band, 1u);
         __syncthreads();
         const int wk = s_item;
         if (wk >= nitems) break;
         const int ps = wk < nfs ? 1 : 0, fsl = wk < nfs ? wk : wk - nfs;
-        k_model_body<kCompact, kRep>(A, band, smem_raw, fsl % A.nslices, ps, fsl / A.nslices);
+        k_model_body<kCompact>(A, band, nframes, smem_raw, fsl % A.nslices, ps, fsl / A.nslices, ph_state, ph_row);
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last table saved has reached global memory
 }
 __global__ void __launch_bounds__(kModelThreads, 1) k_model(const __grid_constant__ EncArgs A, int band, int nframes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_loop<false, true>(A, band, nframes, smem_raw);
-}
-__global__ void __launch_bounds__(kModelThreads, 1) k_model_lean(const __grid_constant__ EncArgs A, int band, int nframes) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_loop<false, false>(A, band, nframes, smem_raw);
+    k_model_loop<false>(A, band, nframes, smem_raw);
 }
 __global__ void __launch_bounds__(kModelThreads, 1) k_model_compact(const __grid_constant__ EncArgs A, int band, int nframes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    k_model_loop<true, false>(A, band, nframes, smem_raw);
+    k_model_loop<true>(A, band, nframes, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1368,10 +1138,10 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const __grid_constant__ E
 
 // ------------------------------------------------------------------------------------------------------------------
 typedef void (*model_fn)(const EncArgs, int, int);
-static model_fn pick_model(const EncArgs& a) { return a.sstride != 32 ? k_model_compact : (a.t1_rep > 0 ? k_model : k_model_lean); }
+static model_fn pick_model(const EncArgs& a) { return a.sstride != 32 ? k_model_compact : k_model; }
 
 cudaError_t configure_kernels(const EncArgs& a) {
-    const size_t need = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.t1_rep, a.stage_cap);
+    const size_t need = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.stage_cap);
     // every kernel asks for the same L1 / shared-memory split as k_model: an SM cannot hold CTAs of two kernels that want
     // different splits, and k_range / k_emit / k_pack must run beside k_model's CTAs, not after them
     cudaFuncSetAttribute(k_range, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1384,7 +1154,7 @@ cudaError_t configure_kernels(const EncArgs& a) {
 }
 
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s) {
-    const size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.t1_rep, a.stage_cap);
+    const size_t smem = model_smem_bytes(a.nctx, a.sstride, a.wmax, 2, a.stage_cap);
     int grid = a.model_ctas;
     if (grid > nframes * a.nslices * 2) grid = nframes * a.nslices * 2;
     pick_model(a)<<<grid, kModelThreads, smem, s>>>(a, band, nframes);

@@ -48,7 +48,6 @@ struct EncArgs {
     int32_t band_rows, nbands, wmax, hmax;
     int32_t stage_cap;            // records of one plane-row segment k_model stages in shared memory
     int32_t nseg;                 // column segments per plane-row reserved in rowcnt (1..kMaxSeg)
-    int32_t t1_rep;              // > 0: one_state table replicated per bank in k_model's shared memory, < 0: plain table
     const SliceGeom* geom;        // [nslices]
     const int16_t* qtab;          // [5][256]
     const uint8_t* t1q;           // [256] t1q[q] = one_state[q + 1]
@@ -85,8 +84,8 @@ struct EncArgs {
     uint32_t* flags;              // [0] overflow flag, [2..3] total bins, [16..] phase cycles (-DB200_PHASE_TIMING)
 };
 
-size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes, int t1_rep);
-size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int t1_rep, int stage_cap);
+size_t model_smem_fixed(int nctx, int sstride, int wmax, int planes);
+size_t model_smem_bytes(int nctx, int sstride, int wmax, int planes, int stage_cap);
 cudaError_t launch_model(const EncArgs& a, int band, int nframes, cudaStream_t s);
 cudaError_t launch_range(const EncArgs& a, int band, int nframes, cudaStream_t s);
 cudaError_t launch_emit(const EncArgs& a, int nframes, cudaStream_t s);
