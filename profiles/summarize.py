@@ -21,6 +21,8 @@ if os.path.exists(p):
     tot, cnt = defaultdict(float), defaultdict(int)
     for r in rows[1:]:
         name = r[ki].split("(")[0]
+        if r[vi].strip().lower() in ("nan", "n/a", ""):      # a launch ncu could not time (seen once per run under green contexts)
+            continue
         tot[name] += float(r[vi].replace(",", "")) / 1e6
         cnt[name] += 1
     total = sum(tot.values())
@@ -41,7 +43,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 traffic = {}
-for k in ("k_model", "k_range", "k_emit", "k_pack"):
+for k in ("k_model", "k_range", "k_emit", "k_pack", "k_flac", "k_decode"):
     rep = os.path.join(G, "%s_%s.ncu-rep" % (tag, k))
     if not os.path.exists(rep):
         continue

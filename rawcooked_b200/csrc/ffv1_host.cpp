@@ -135,6 +135,7 @@ class HostRangeEncoder {
     std::vector<uint8_t> bytes_;
 };
 
+}  // namespace
 // default transition table of the FFV1 range coder (the reference holds it as a literal,
 // Source/Lib/CoDec/FFV1/FFV1_Frame.cpp:35-55; generated here from its defining recurrence, p += (1-p)*0.05)
 void default_one_state(uint8_t one[256]) {
@@ -161,6 +162,7 @@ void default_one_state(uint8_t one[256]) {
         one[i] = (uint8_t)p8;
     }
 }
+namespace {
 
 // transition table sent on the wire for `-coder 1` (coder_type 2): the table ffmpeg sends, so that packets are
 // byte-identical to the reference pipeline's (read back by parameters::Parse, FFV1_Parameters.cpp:41-55)

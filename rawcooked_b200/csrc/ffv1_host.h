@@ -41,6 +41,7 @@ int slice_grid(uint32_t width, uint32_t height, int slices, int bits, int* num_h
 // returns 0 or a negative b200_status; fills err
 int build_stream(uint32_t width, uint32_t height, int layout, int slices, int context, int ec, Ffv1Stream* out, const char** err);
 
+void default_one_state(uint8_t one[256]);   // default state transitions (FFV1_Frame.cpp:35-55)
 uint32_t crc32_mpeg(const uint8_t* d, size_t n, uint32_t crc = 0);
 const uint32_t* crc32_mpeg_table();
 

@@ -13,15 +13,20 @@ ROOT = util.ROOT
 
 
 def declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "b200enc.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr)))
+    syms = set()
+    for name in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not name.endswith(".h"):
+            continue
+        hdr = open(os.path.join(ROOT, "include", name)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        syms |= set(re.findall(r"\b(b200(?:enc)?_[a-z0-9_]+)\s*\(", hdr))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol():
     L = ffv1.load_library()
     syms = declared_symbols()
-    assert len(syms) >= 12
+    assert len(syms) >= 30 and "b200_ffv1_check_host" in syms and "b200enc_main" in syms
     for s in syms:
         assert hasattr(L, s), "libb200enc.so does not export %s" % s
 
@@ -80,3 +85,38 @@ def test_host_config_record_equals_ffmpeg_golden():
         assert ffv1.config_record(w, h, layout, slices=slices, context=context, slicecrc=ec) == rec, (i, w, h, layout, slices, context, ec)
     with pytest.raises(ffv1.B200Error):
         ffv1.config_record(1920, 1080, S.DPX_RGB_16_BE, slices=7)
+
+
+def test_config_record_parser_reads_ffmpeg_and_own_records():
+    # parameters::Parse on the host (the decoder's side of the ConfigurationRecord): libavcodec's golden records and the
+    # encoder's own must read back as the option set that produced them
+    import util
+    from rawcooked_b200 import ffv1dec
+    for i in range(util.golden_count()):
+        w, h, layout, slices, context, ec, _, rec, _ = util.golden_case(i)
+        nh, nv = ffv1.slice_grid(w, h, slices)
+        for r in (rec, ffv1.config_record(w, h, layout, slices=slices, context=context, slicecrc=ec)):
+            p = ffv1dec.parse_config_record(r)
+            assert (p.version, p.micro_version, p.coder_type, p.colorspace_type) == (3, 4, 2, 1)
+            assert p.bits_per_raw_sample == S.LAYOUT_BITS[layout]
+            assert (p.chroma_planes, p.alpha_plane, p.log2_h_chroma_subsample, p.log2_v_chroma_subsample) == (1, 0, 0, 0)
+            assert (p.num_h_slices, p.num_v_slices, p.ec, p.intra, p.quant_table_set_count, p.crc_ok) == (nh, nv, ec, 1, 2, 1)
+            small, large = ((11 ** 3 + 1) // 2, (11 * 11 * 125 + 1) // 2) if p.bits_per_raw_sample == 8 else ((9 ** 3 + 1) // 2, (9 * 9 * 125 + 1) // 2)
+            assert list(p.context_count)[:2] == [small, large]
+    # a flipped bit is caught by the record's CRC, with the reference's error text
+    bad = bytearray(rec)
+    bad[5] ^= 4
+    with pytest.raises(ffv1.B200Error, match="configuration_record_crc_parity"):
+        ffv1dec.parse_config_record(bytes(bad))
+
+
+def test_decoder_needs_a_device():
+    import util
+    from rawcooked_b200 import ffv1dec
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    w, h, layout, slices, context, ec, _, rec, _ = util.golden_case(0)
+    with pytest.raises(ffv1.B200Error) as e:
+        ffv1dec.FFV1Decoder(w, h, layout, rec)
+    assert e.value.code == -2
