@@ -41,7 +41,7 @@ typedef struct b200_ffv1_dec_cfg {
     int32_t  layout;            /* b200_layout of the payload to produce / compare with; its bit depth must equal the stream's */
     int32_t  max_frames;        /* frames per call (>= 1) */
     int32_t  device;
-    int32_t  slices_per_warp;   /* 0 = default (B200_DEC_SPW or 4); 1..32: slices that share a warp, one lane each */
+    int32_t  slices_per_warp;   /* 0 = chosen per call from the slices in flight (or B200_DEC_SPW); 1..32: slices that share a warp, one lane each */
     int32_t  reserved[6];       /* must be 0 */
 } b200_ffv1_dec_cfg;
 

@@ -105,9 +105,9 @@ int b200_ffv1_dec_open(const b200_ffv1_dec_cfg* cfg, const uint8_t* record, size
     A.swap_bg = S.bits > 8 && S.bits < 16;
     A.num_h = S.num_h; A.num_v = S.num_v; A.nslices = S.num_h * S.num_v; A.ec = S.ec; A.tail = S.ec ? 8 : 3; A.nsets = S.nsets;
     int spw = cfg->slices_per_warp;
-    if (!spw) { const char* e = std::getenv("B200_DEC_SPW"); spw = e ? std::atoi(e) : 4; }
-    if (spw < 1 || spw > 32) { delete D; return dfail(B200_ERR_INVALID, "slices_per_warp must be 1..32"); }
-    A.spw = spw;
+    if (!spw) { const char* e = std::getenv("B200_DEC_SPW"); spw = e ? std::atoi(e) : 0; }
+    if (spw < 0 || spw > 32) { delete D; return dfail(B200_ERR_INVALID, "slices_per_warp must be 1..32"); }
+    A.spw = spw;     // 0: chosen per call from the number of slices in flight
     A.maxctx = 0;
     for (int i = 0; i < S.nsets; i++) { A.nctx[i] = S.nctx[i]; if (S.nctx[i] > A.maxctx) A.maxctx = S.nctx[i]; }
     A.row_bytes = (uint32_t)b200::layout_row_bytes(cfg->width, cfg->layout);
@@ -184,6 +184,13 @@ int b200_ffv1_decode_device(b200_ffv1_dec* D, const void* d_packets, const size_
     for (int i = 0; i < n; i++) { D->h_meta[i] = pkt_off[i]; D->h_meta[n + i] = pkt_len[i]; }
     DCU(cudaMemcpyAsync(D->d_off, D->h_meta, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     DCU(cudaMemcpyAsync(D->d_len, D->h_meta + n, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (!A.spw) {
+        // a lane is latency-bound (one dependent instruction every ~4.6 cycles), so the more warps in flight the better, up to
+        // one wave: 148 SMs x 16 warps at 128 registers per thread. Beyond that, slices share warps.
+        const int total = n * A.nslices, wave = 148 * 16;
+        A.spw = (total + wave - 1) / wave;
+        if (A.spw > 8) A.spw = 8;
+    }
     A.packets = static_cast<const uint8_t*>(d_packets);
     A.out = static_cast<uint8_t*>(d_out);
     A.cmp = static_cast<const uint8_t*>(d_sources);
