@@ -491,6 +491,47 @@ def run_b200(args):
     enc.packets_device(F)
     ts = enc.stats()
     enc.set_timing(False)
+    # ---- decode + compare leg (the `--check` side): the packets of that pass, still in the encoder's arena, are
+    # decoded by k_decode and compared on the GPU with the frames they were coded from; beside it the reference's own decoder
+    # (oracle/_ref: ffv1_frame::Process, slice-threaded as `rawcooked --check` runs it) on one of the packets
+    decode_stats = None
+    if rank == 0 and world == 1 and not args.no_decode:
+        from rawcooked_b200 import ffv1dec
+        arena, d_offs, d_lens = enc.packets_device(F)
+        dec = ffv1dec.FFV1Decoder(W, H, layout, enc.config_record, max_frames=F, device=local)
+        best = None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dec.decode_device(arena, d_offs, d_lens, d_sources=d_frames.data_ptr(), stream=stream.cuda_stream)
+            mm, stt = dec.result(F)
+            dtd = time.perf_counter() - t0
+            best = dtd if best is None else min(best, dtd)
+        ds = dec.stats()
+        dec.close()
+        decode_stats = {"what": "b200_ffv1_decode_device: packets in the encoder's device arena -> k_dec_index + k_decode -> compare with the device "
+                                "frames (inverse RCT + byte layout + compare on the GPU)",
+                        "frames": F, "ms": best * 1e3, "fps": F / best, "MPix_per_s": F * W * H / best / 1e6, "k_decode_ms": ds["decode_us"] / 1e3,
+                        "mismatching_bytes": int(sum(mm)), "status_bits": int(max(stt)), "samples": int(ds["samples"]),
+                        "cycles_per_sample_per_slice": ds["decode_us"] * 1e-6 * 1.965e9 / (ds["samples"] / max(1, ds["slices"]))}
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import util
+            if util.ref_available():
+                ncores = os.cpu_count() or 1
+                pk0 = np.empty(d_lens[0], np.uint8)
+                torch.cuda.synchronize()
+                pk0[:] = torch.as_tensor(_CudaBuf(arena + d_offs[0], d_lens[0]), device=dev).cpu().numpy()
+                src0 = d_frames[0].cpu().numpy().tobytes()
+                t0 = time.perf_counter()
+                same = util.ref_decode(enc.config_record, pk0.tobytes(), W, H, layout, threads=ncores) == src0
+                dtr = time.perf_counter() - t0
+                decode_stats["cpu_reference"] = {"what": "reference decoder (oracle/_ref, unmodified ffv1_frame::Process + Transform), one frame, "
+                                                         "slice threads = %d" % ncores, "s_per_frame": dtr, "fps": 1.0 / dtr,
+                                                 "equals_input": bool(same)}
+                decode_stats["speedup_vs_cpu_reference"] = (F / best) * dtr
+        if decode_stats["mismatching_bytes"] or decode_stats["status_bits"]:
+            check = "FAIL"
     if flac_enc is not None and rank == 0:
         # FLAC leg alone: whole-call time (H2D + k_flac + D2H) and the kernel share, SURVEY §8d: in = samples*ch*3 B, out = packet bytes
         torch.cuda.synchronize()
@@ -559,6 +600,8 @@ def run_b200(args):
         }
         if flac_stats is not None:
             line["flac"] = flac_stats
+        if decode_stats is not None:
+            line["decode_check"] = decode_stats
         print(json.dumps(line), flush=True)
     enc.close()
     if flac_enc is not None:
@@ -586,6 +629,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle / reference-decoder check of the timed packets")
     ap.add_argument("--check-frames", type=int, default=3)
+    ap.add_argument("--no-decode", action="store_true", help="skip the decode + compare leg (k_decode on the packets of the last pass)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../include/b200dec.h"
 #include "../../include/b200enc.h"
 #include "ingest.h"
 #include "mkv_mux.h"
@@ -147,6 +149,9 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
     const size_t fb = b200_ffv1_frame_bytes(v.info.width, v.info.height, v.info.layout);
     const size_t N = v.files.size();
     const size_t B = std::min<size_t>((size_t)frames_in_flight, N);
+    const char* ve = getenv("B200_VERIFY");
+    const bool verify = ve && atoi(ve) > 0;
+    std::atomic<size_t> verified{0};
     const size_t nbatch = (N + B - 1) / B;
     const size_t G = std::max<size_t>(1, std::min(devices.size(), nbatch));
     VideoPipeline P;
@@ -206,6 +211,18 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
             cfg.max_frames = (int32_t)B; cfg.device = device;
             if (b200_ffv1_open(&cfg, &E)) { fail_all(std::string("ffv1: ") + b200_last_error()); return; }
         }
+        // B200_VERIFY=1: every packet is decoded again on the GPU (k_decode, the `--check` decoder of include/b200dec.h) and
+        // compared with the source payload it was coded from, while the next batch is being coded; any difference fails the job
+        b200_ffv1_dec* D = nullptr;
+        if (verify) {
+            std::vector<uint8_t> rec(b200_ffv1_config_record(E, nullptr, 0));
+            b200_ffv1_config_record(E, rec.data(), rec.size());
+            b200_ffv1_dec_cfg dc;
+            memset(&dc, 0, sizeof dc);
+            dc.width = v.info.width; dc.height = v.info.height; dc.layout = v.info.layout; dc.max_frames = (int32_t)B; dc.device = device;
+            if (b200_ffv1_dec_open(&dc, rec.data(), rec.size(), &D)) { b200_ffv1_close(E); fail_all(std::string("verify: ") + b200_last_error()); return; }
+        }
+        struct DecGuard { b200_ffv1_dec*& d; ~DecGuard() { if (d && !g_fast_exit) b200_ffv1_dec_close(d); } } dec_guard{D};
         PinnedBuf in[2], out[2];
         // pinning is slow (a few GB/s): only the first input buffer is pinned before work starts; the second one and the
         // output buffers are pinned by background threads while the first batch is read and coded, each joined where its
@@ -238,6 +255,22 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
             }
             if (!join_bg(1 + (int)(jj & 1)) || !o.ensure(total)) { werr = "cannot allocate pinned host buffers"; return false; }
             if (b200_ffv1_fetch_packets(E, o.p, o.cap, bt.off.data(), bt.len.data(), (int32_t)bt.n)) { werr = std::string("ffv1 fetch: ") + b200_last_error(); return false; }
+            if (D) {
+                std::vector<const uint8_t*> pk(bt.n), src(bt.n);
+                std::vector<uint64_t> mm(bt.n);
+                std::vector<uint32_t> st(bt.n);
+                for (size_t i = 0; i < bt.n; i++) { pk[i] = o.p + bt.off[i]; src[i] = in[jj & 1].p + i * fb; }
+                if (b200_ffv1_check_host(D, pk.data(), bt.len.data(), (int32_t)bt.n, src.data(), mm.data(), st.data())) {
+                    werr = std::string("verify: ") + b200_last_error();
+                    return false;
+                }
+                for (size_t i = 0; i < bt.n; i++)
+                    if (mm[i] || st[i]) {
+                        werr = "verify: " + v.files[bt.f0 + i] + " does not decode to itself (" + std::to_string(mm[i]) + " bytes differ, decoder status " + std::to_string(st[i]) + ")";
+                        return false;
+                    }
+                verified += bt.n;
+            }
             {
                 std::lock_guard<std::mutex> lk(P.mu);
                 bt.data = o.p;
@@ -309,6 +342,8 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
         P.cv.notify_all();
     }
     for (auto& t : workers) t.join();
+    if (!rc && verify)
+        fprintf(stderr, "b200enc: %zu of %zu frames decoded again on the GPU and compared with their source payloads: no difference\n", verified.load(), N);
     return rc;
 }
 

@@ -188,3 +188,19 @@ def ffv1_grid(w, h, mkv_bytes):
         if rec in mkv_bytes:
             return ffv1.slice_grid(w, h, slices)
     raise AssertionError("no known ConfigurationRecord in the MKV")
+
+
+@pytest.mark.parametrize("env", [
+    {"B200_VERIFY": "1", "B200_FRAMES_IN_FLIGHT": "3"},
+    {"B200_VERIFY": "1", "B200_FRAMES_IN_FLIGHT": "2", "B200_DEVICES": "0,0"},
+], ids=["one_worker", "two_workers"])
+def test_encode_time_verification_on_the_gpu(tmp_path, env):
+    # B200_VERIFY=1: every packet is decoded again by the CUDA decoder (include/b200dec.h) and compared with its source payload
+    # while the next batch is coded; the reference's own --check then confirms the same thing on the CPU
+    name = "verify"
+    n = 8
+    write_dpx_sequence(str(tmp_path / name), n, 320, 240, S.DPX_RGB_16_BE, 4000)
+    code, out = run_rawcooked_env(["--check", "-y", "-b", B200ENC, "-slices", "24", name], str(tmp_path), env)
+    assert code == 0, out
+    assert OK in out, out
+    assert "%d of %d frames decoded again on the GPU" % (n, n) in out, out
