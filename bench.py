@@ -532,6 +532,50 @@ def run_b200(args):
                 decode_stats["speedup_vs_cpu_reference"] = (F / best) * dtr
         if decode_stats["mismatching_bytes"] or decode_stats["status_bits"]:
             check = "FAIL"
+    # ---- analysis leg: MD5 of the F payloads as `rawcooked --hash` hashes its input files (one lane per file),
+    # and the padding-bit test of `--check-padding` where the layout has padding bits; beside it the reference's md5.c on one core
+    analysis_stats = None
+    if rank == 0 and world == 1 and not args.no_decode:
+        from rawcooked_b200 import scan
+        sc = scan.Scanner(max_items=F, max_bytes=0, device=local)
+        best = None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            digs = sc.md5_device(d_frames.data_ptr(), [i * fb for i in range(F)], [fb] * F, stream=stream.cuda_stream)
+            dta = time.perf_counter() - t0
+            best = dta if best is None else min(best, dta)
+        import hashlib
+        md5_ok = digs[0] == hashlib.md5(d_frames[0].cpu().numpy().tobytes()).digest() and digs[F - 1] == hashlib.md5(d_frames[F - 1].cpu().numpy().tobytes()).digest()
+        analysis_stats = {"md5": {"what": "b200_md5_device: k_md5, one lane per file, %d payloads of %d bytes resident in HBM" % (F, fb),
+                                  "ms": best * 1e3, "GB_per_s": F * fb / best / 1e9, "files_per_s": F / best, "equals_hashlib": bool(md5_ok)}}
+        if layout < 32:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            cntp, firstp = sc.padding_device(W, H, layout, d_frames.data_ptr(), F, stream=stream.cuda_stream)
+            dtp = time.perf_counter() - t0
+            stp = sc.stats()
+            analysis_stats["padding"] = {"what": "b200_padding_device: the test of DPX.cpp:500-608 on the same payloads", "ms": dtp * 1e3,
+                                         "kernel_ms": stp["kernel_us"] / 1e3, "bytes_read": int(stp["bytes"]),
+                                         "GB_per_s": (stp["bytes"] / (stp["kernel_us"] * 1e-6) / 1e9) if stp["kernel_us"] else None,
+                                         "payloads_with_nonzero_padding": int(sum(1 for v in cntp if v))}
+        sc.close()
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import util
+            if util.ref_available():
+                R = util.ref_decoder()
+                R.ref_md5.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+                one = d_frames[0].cpu().numpy()
+                outb = C.create_string_buffer(16)
+                t0 = time.perf_counter()
+                R.ref_md5(one.ctypes.data, one.size, outb)
+                dtr = time.perf_counter() - t0
+                analysis_stats["md5"]["cpu_reference"] = {"what": "the reference's md5.c (oracle/_ref), one core, one payload", "GB_per_s": one.size / dtr / 1e9,
+                                                          "files_per_s": 1.0 / dtr, "equals_gpu": outb.raw == digs[0]}
+                analysis_stats["md5"]["speedup_vs_one_core"] = (F / best) * dtr
+        if not md5_ok:
+            check = "FAIL"
     if flac_enc is not None and rank == 0:
         # FLAC leg alone: whole-call time (H2D + k_flac + D2H) and the kernel share, SURVEY §8d: in = samples*ch*3 B, out = packet bytes
         torch.cuda.synchronize()
@@ -602,6 +646,8 @@ def run_b200(args):
             line["flac"] = flac_stats
         if decode_stats is not None:
             line["decode_check"] = decode_stats
+        if analysis_stats is not None:
+            line["analysis"] = analysis_stats
         print(json.dumps(line), flush=True)
     enc.close()
     if flac_enc is not None:

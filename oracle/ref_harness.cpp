@@ -123,3 +123,22 @@ int ref_flac_decode(const uint8_t* stream, size_t size, int32_t* out, size_t cap
     return (!ok || m.error) ? 1 : (m.n > m.cap ? 2 : 0);
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MD5 as input_base::Hash computes it for --hash (Source/Lib/Utils/FileIO/Input_Base.cpp:54-81) with the reference's
+// vendored md5.c (Source/Lib/ThirdParty/md5)
+extern "C" {
+#include "md5.h"
+void ref_md5(const uint8_t* data, size_t size, uint8_t out[16])
+{
+    MD5_CTX c;
+    MD5_Init(&c);
+    size_t off = 0;
+    while (off < size) {
+        unsigned long n = size - off > 0x40000000ul ? 0x40000000ul : (unsigned long)(size - off);
+        MD5_Update(&c, data + off, n);
+        off += n;
+    }
+    MD5_Final(out, &c);
+}
+}

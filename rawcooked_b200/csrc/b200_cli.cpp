@@ -474,6 +474,10 @@ extern "C" int b200enc_main(int argc, char** argv) {
         }
     }
 
+    // one video track per file: a second one would be muxed after the first (timestamps restarting at 0, clusters out of order).
+    // RAWcooked emits one image sequence per package in every flow this front-end is tested with; refuse rather than write that
+    if (videos.size() > 1) return fail("more than one video input: only one image sequence per output file is supported");
+
     // ---- attachments
     std::vector<b200::MkvAttachment> atts;
     for (const AttachSpec& a : attaches) {
