@@ -392,13 +392,8 @@ __device__ uint32_t pack_row(const DecArgs& A, int lane, int frame, int x0, int 
 struct DecSmem {
     int16_t* qtab; uint8_t* trans; uint32_t* crc; uint8_t* rows;
 };
-// Per slice, a direct-mapped cache of context-state rows in shared memory in front of the table in global memory (2 x 162 KB
-// per slice with the large context model): the rows a slice keeps coming back to are a few dozen. Frames are intra-only, so
-// nothing has to be written back when the slice ends.
-__host__ __device__ inline int dec_cache_rows(int spw) { return spw <= 4 ? 64 : spw <= 8 ? 32 : spw <= 16 ? 16 : 8; }
-__host__ __device__ inline size_t dec_cache_bytes(int spw) { return (size_t)dec_cache_rows(spw) * 36 + 16; }   // rows, tags, 16 bytes of bank skew
-__host__ __device__ inline size_t dec_smem_bytes(int nsets, int spw) {
-    return (size_t)nsets * 5 * 256 * 2 + 512 + 1024 + (size_t)kDecWarpsPerCta * 32 * kRowStride + (size_t)kDecWarpsPerCta * spw * dec_cache_bytes(spw);
+__host__ __device__ inline size_t dec_smem_bytes(int nsets, int) {
+    return (size_t)nsets * 5 * 256 * 2 + 512 + 1024 + (size_t)kDecWarpsPerCta * 32 * kRowStride;
 }
 
 __global__ void __launch_bounds__(32 * kDecWarpsPerCta, B200_DEC_MIN_CTAS) k_decode(const __grid_constant__ DecArgs A, int nframes) {
@@ -416,11 +411,6 @@ __global__ void __launch_bounds__(32 * kDecWarpsPerCta, B200_DEC_MIN_CTAS) k_dec
     const uint32_t tt_a = smem_a(S.trans), qtab_a = smem_a(S.qtab);   // tt: (next state after 0) | (next state after 1) << 8
     const uint32_t row_a = smem_a(S.rows) + (uint32_t)((warp * 32 + lane) * kRowStride);
     const int spw = A.spw;
-    // this lane's row cache: NR rows of 32 bytes, then NR tags (plane-set << 16 | context; all ones: empty)
-    const int NR = dec_cache_rows(spw);
-    const int cache_shift = 32 - (31 - __clz(NR));
-    uint8_t* cache_p = S.rows + (size_t)kDecWarpsPerCta * 32 * kRowStride + (size_t)(warp * spw + (lane < spw ? lane : 0)) * dec_cache_bytes(spw);
-    uint32_t* ctags = reinterpret_cast<uint32_t*>(cache_p + (size_t)NR * 32);
     const int total = nframes * A.nslices;
     const int wid = blockIdx.x * kDecWarpsPerCta + warp;
     const size_t line_stride = (size_t)9 * A.wpad;            // ints per slice: [plane][row % 3][wpad]
@@ -475,7 +465,6 @@ __global__ void __launch_bounds__(32 * kDecWarpsPerCta, B200_DEC_MIN_CTAS) k_dec
         const uint8_t* p = A.packets + A.sl_off[sidx];
         slice_bytes = A.sl_size[sidx];
         slice_p = p;
-        for (int i = 0; i < NR; i++) ctags[i] = 0xFFFFFFFFu;
         rc_init(rc, p, slice_bytes - (uint32_t)A.tail);
         for (int i = 0; i < 8; i++) reinterpret_cast<uint32_t*>(S.rows + (size_t)(warp * 32 + lane) * kRowStride)[i] = 0x80808080u;
         if (A.sl_off[sidx] == A.pkt_off[frame]) {               // first slice of the packet: the keyframe bin (FFV1_Slice.cpp:221-225)
@@ -519,7 +508,6 @@ __global__ void __launch_bounds__(32 * kDecWarpsPerCta, B200_DEC_MIN_CTAS) k_dec
     bool fresh = true;                          // (x == 0): row pointers and border values must be set up
     bool rowdone = false;
 
-    int cslot = 0;                              // cache row that is the home of the row in R
     if (!active) rc_dead(rc);
     while (__any_sync(0xffffffffu, active)) {
         // ---- phase A (lanes with a slice): neighbours, context, state row of the context
@@ -553,31 +541,18 @@ __global__ void __launch_bounds__(32 * kDecWarpsPerCta, B200_DEC_MIN_CTAS) k_dec
             if (neg) ctx = -ctx;
             const int want = ((pl ? 1 : 0) << 16) | ctx;
             if (want != cached) {
-                // the row in R goes home to its cache row; the wanted row comes from the cache, or from the table in global
-                // memory after the row that held its place has been written back there
+                // the row in R goes back to the table in global memory, the wanted one comes from there. (A direct-mapped cache
+                // of rows in shared memory in front of the table was measured: on noisy 16-bit material the quantised context is
+                // spread over all 10 126 rows, 94 % of the look-ups missed and the bookkeeping cost more than it saved.)
                 if (cached >= 0) {
-                    uint4* h = reinterpret_cast<uint4*>(cache_p + (size_t)cslot * 32);
-                    h[0] = make_uint4(R.out[0], R.out[1], R.out[2], R.out[3]);
-                    h[1] = make_uint4(R.out[4], R.out[5], R.out[6], R.out[7]);
+                    uint4* g = reinterpret_cast<uint4*>(states + (size_t)(cached >> 16) * state_stride + (size_t)(cached & 0xFFFF) * 32);
+                    g[0] = make_uint4(R.out[0], R.out[1], R.out[2], R.out[3]);
+                    g[1] = make_uint4(R.out[4], R.out[5], R.out[6], R.out[7]);
                 }
-                const int ns = (int)(((uint32_t)want * 2654435761u) >> cache_shift);
-                const uint32_t tag = ctags[ns];
-                uint4 a, b;
-                if (tag == (uint32_t)want) {
-                    const uint4* h = reinterpret_cast<const uint4*>(cache_p + (size_t)ns * 32);
-                    a = h[0]; b = h[1];
-                } else {
-                    if (tag != 0xFFFFFFFFu) {
-                        const uint4* h = reinterpret_cast<const uint4*>(cache_p + (size_t)ns * 32);
-                        uint4* g = reinterpret_cast<uint4*>(states + (size_t)(tag >> 16) * state_stride + (size_t)(tag & 0xFFFFu) * 32);
-                        g[0] = h[0]; g[1] = h[1];
-                    }
-                    const uint4* g = reinterpret_cast<const uint4*>(states + (size_t)(want >> 16) * state_stride + (size_t)ctx * 32);
-                    a = g[0]; b = g[1];
-                    ctags[ns] = (uint32_t)want;
-                }
+                const uint4* g = reinterpret_cast<const uint4*>(states + (size_t)(want >> 16) * state_stride + (size_t)ctx * 32);
+                const uint4 a = g[0], b = g[1];
                 R.out[0] = a.x; R.out[1] = a.y; R.out[2] = a.z; R.out[3] = a.w; R.out[4] = b.x; R.out[5] = b.y; R.out[6] = b.z; R.out[7] = b.w;
-                cached = want; cslot = ns;
+                cached = want;
             }
         }
 #pragma unroll

@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(kFlacThreads) k_flac(const __grid_constant__ F
     int32_t* xw = reinterpret_cast<int32_t*>(smem_raw) + 2 * A.block_size;
     __shared__ LpcSet s_lpc;
     __shared__ long long s_ac[kLpcMaxOrder + 1];
-    __shared__ int s_lpc_m, s_lpc_bp;
     __shared__ unsigned int s_lpc_bad;
     __shared__ unsigned long long s_S[512];          // partition sums, level p at [2^p - 1 ...]
     __shared__ uint8_t s_k[512];                     // Rice parameter per partition, same indexing
@@ -332,7 +331,9 @@ __global__ void __launch_bounds__(kFlacThreads) k_flac(const __grid_constant__ F
                     __syncthreads();
                     const unsigned long long S = lpc_residual(m, false);
                     __syncthreads();
-                    if (s_lpc_bad) continue;
+                    const uint32_t overflowed = s_lpc_bad;              // read by everyone before thread 0 clears it for the next order
+                    __syncthreads();
+                    if (overflowed) continue;
                     const unsigned long long cntm = (unsigned long long)(n - m);
                     int k = 0;
                     while (k < 30 && (cntm << (k + 1)) <= S) k++;
