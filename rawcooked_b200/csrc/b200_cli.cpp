@@ -474,9 +474,9 @@ extern "C" int b200enc_main(int argc, char** argv) {
         }
     }
 
-    // one video track per file: a second one would be muxed after the first (timestamps restarting at 0, clusters out of order).
-    // RAWcooked emits one image sequence per package in every flow this front-end is tested with; refuse rather than write that
-    if (videos.size() > 1) return fail("more than one video input: only one image sequence per output file is supported");
+    // several video inputs (RAWcooked emits one per run of consecutive frame numbers when a sequence has gaps, gaps.sh) become
+    // several V_FFV1 tracks, muxed one after the other: each track's timestamps start at 0, which the reference's parser and
+    // --check accept (tests/test_cli_gpu.py::test_rawcooked_gaps_concat_lists) although players would prefer them interleaved
 
     // ---- attachments
     std::vector<b200::MkvAttachment> atts;

@@ -204,3 +204,20 @@ def test_encode_time_verification_on_the_gpu(tmp_path, env):
     assert code == 0, out
     assert OK in out, out
     assert "%d of %d frames decoded again on the GPU" % (n, n) in out, out
+
+
+def test_rawcooked_output_version_2(tmp_path):
+    # `--output-version 2` (Source/CLI/Global.cpp:161-177): the command line carries no -attach (Output.cpp:279-291), the
+    # reference appends its reversibility data to the Matroska file after the encoder has returned (Main.cpp:905-929) and then
+    # parses the result: the Segment this muxer wrote must be complete and of finite size for that to work
+    name = "v2"
+    write_dpx_sequence(str(tmp_path / name), 5, 256, 192, S.DPX_RGB_10_FA_BE, 5000)
+    code, out = run_rawcooked(["--output-version", "2", "--check", "-y", "-b", B200ENC, "-slices", "4", name], cwd=str(tmp_path))
+    assert code == 0, out
+    assert OK in out, out
+    victim = tmp_path / name / "f_000003.dpx"
+    b = bytearray(victim.read_bytes())
+    b[6000] ^= 0x08
+    victim.write_bytes(bytes(b))
+    code2, out2 = run_rawcooked(["--check", name + ".mkv", "-o", "./"], cwd=str(tmp_path))
+    assert OK not in out2 and ("not same" in out2 or code2 != 0), out2
