@@ -48,6 +48,17 @@ int b200_padding_host(b200_scan* s, uint32_t width, uint32_t height, int32_t lay
 int b200_padding_device(b200_scan* s, uint32_t width, uint32_t height, int32_t layout, const void* d_payloads, int32_t n,
                         uint64_t* nonzero, uint64_t* first, void* d_masked, void* stream);
 
+/* `-f framemd5` (the second output RAWcooked adds with --framemd5, Source/CLI/Output.cpp:312-332): MD5 of every frame as
+ * FFmpeg's rawvideo encoder emits it, i.e. in the pix_fmt its dpx / tiff decoder produces for the flavor (8 bit: rgb24;
+ * 10 / 12 bit: gbrp10le / gbrp12le, planes G, B, R; 16 bit: rgb48le / rgb48be by the file's byte order), rows without padding.
+ * b200_rawvideo_bytes() is the `size` column of the framemd5 file, b200_rawvideo_pix_fmt() the pix_fmt name. */
+size_t b200_rawvideo_bytes(uint32_t width, uint32_t height, int32_t layout);
+const char* b200_rawvideo_pix_fmt(int32_t layout);
+int b200_framemd5_host(b200_scan* s, uint32_t width, uint32_t height, int32_t layout, const uint8_t* const* payloads, int32_t n,
+                       uint8_t* digests);
+int b200_framemd5_device(b200_scan* s, uint32_t width, uint32_t height, int32_t layout, const void* d_payloads, int32_t n,
+                         uint8_t* digests, void* stream);
+
 /* Device time in microseconds of the last call's kernel ([0]) and bytes it read ([1]). */
 int b200_scan_stats(const b200_scan* s, uint64_t stats[4]);
 

@@ -27,6 +27,7 @@
 
 #include "../../include/b200dec.h"
 #include "../../include/b200enc.h"
+#include "../../include/b200scan.h"
 #include "ingest.h"
 #include "mkv_mux.h"
 
@@ -68,10 +69,24 @@ double parse_rate(const std::string& s) {
     return d ? atof(s.substr(0, sl).c_str()) / d : 0;
 }
 
+// "24", "24000/1001" or "23.976" as a reduced fraction (the time base of a framemd5 output is its inverse)
+void parse_rate_q(const std::string& s, long long* num, long long* den) {
+    long long n = 0, d = 1;
+    const size_t sl = s.find('/');
+    if (sl != std::string::npos) { n = atoll(s.c_str()); d = atoll(s.c_str() + sl + 1); }
+    else if (s.find('.') != std::string::npos) { n = llround(atof(s.c_str()) * 1000000.0); d = 1000000; }
+    else n = atoll(s.c_str());
+    if (n <= 0 || d <= 0) { n = 25; d = 1; }
+    long long a = n, b = d;
+    while (b) { const long long t = a % b; a = b; b = t; }
+    *num = n / a; *den = d / a;
+}
+
 struct VideoStream {
     std::vector<std::string> files;
     b200::ImageInfo info;
     double fps = 24;
+    long long fps_num = 24, fps_den = 1;
     char kind = 'd';
     int track = 0;
 };
@@ -145,7 +160,8 @@ struct PinnedBuf {
 
 template <class FlushAudio>
 int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vector<int>& devices, int frames_in_flight, unsigned nthreads,
-                        int slices, int context, int slicecrc, b200::MkvWriter& mux, FlushAudio& flush_audio_until, PhaseClock& pc, std::string* err) {
+                        int slices, int context, int slicecrc, b200::MkvWriter& mux, FlushAudio& flush_audio_until, PhaseClock& pc, std::string* err,
+                        std::vector<uint8_t>* frame_md5 /* null, or 16 bytes per frame: the digests of a framemd5 output */) {
     const size_t fb = b200_ffv1_frame_bytes(v.info.width, v.info.height, v.info.layout);
     const size_t N = v.files.size();
     const size_t B = std::min<size_t>((size_t)frames_in_flight, N);
@@ -223,6 +239,10 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
             if (b200_ffv1_dec_open(&dc, rec.data(), rec.size(), &D)) { b200_ffv1_close(E); fail_all(std::string("verify: ") + b200_last_error()); return; }
         }
         struct DecGuard { b200_ffv1_dec*& d; ~DecGuard() { if (d && !g_fast_exit) b200_ffv1_dec_close(d); } } dec_guard{D};
+        // `-f framemd5`: MD5 of every frame in FFmpeg's rawvideo form (k_rawframe + k_md5, include/b200scan.h), one lane per frame
+        b200_scan* Sc = nullptr;
+        if (frame_md5 && b200_scan_open(device, (int32_t)B, fb * B, &Sc)) { b200_ffv1_close(E); fail_all(std::string("framemd5: ") + b200_last_error()); return; }
+        struct ScanGuard { b200_scan*& s; ~ScanGuard() { if (s && !g_fast_exit) b200_scan_close(s); } } scan_guard{Sc};
         PinnedBuf in[2], out[2];
         // pinning is slow (a few GB/s): only the first input buffer is pinned before work starts; the second one and the
         // output buffers are pinned by background threads while the first batch is read and coded, each joined where its
@@ -255,6 +275,14 @@ int encode_video_stream(VideoStream& v, b200_ffv1_enc* first_enc, const std::vec
             }
             if (!join_bg(1 + (int)(jj & 1)) || !o.ensure(total)) { werr = "cannot allocate pinned host buffers"; return false; }
             if (b200_ffv1_fetch_packets(E, o.p, o.cap, bt.off.data(), bt.len.data(), (int32_t)bt.n)) { werr = std::string("ffv1 fetch: ") + b200_last_error(); return false; }
+            if (Sc) {
+                std::vector<const uint8_t*> src(bt.n);
+                for (size_t i = 0; i < bt.n; i++) src[i] = in[jj & 1].p + i * fb;
+                if (b200_framemd5_host(Sc, v.info.width, v.info.height, v.info.layout, src.data(), (int32_t)bt.n, frame_md5->data() + 16 * bt.f0)) {
+                    werr = std::string("framemd5: ") + b200_last_error();
+                    return false;
+                }
+            }
             if (D) {
                 std::vector<const uint8_t*> pk(bt.n), src(bt.n);
                 std::vector<uint64_t> mm(bt.n);
@@ -359,6 +387,7 @@ extern "C" int b200enc_main(int argc, char** argv) {
     std::vector<AttachSpec> attaches;
     std::map<std::string, std::string> pending, outopt;
     std::vector<std::string> outputs;
+    std::string framemd5_path;
     bool overwrite = false, never = false;
     int cur_attach = -1;
     bool after_inputs = false;
@@ -384,14 +413,21 @@ extern "C" int b200enc_main(int argc, char** argv) {
             (void)after_inputs;
             continue;
         }
-        // a bare token is an output file; the options gathered since the last -i / output belong to it
-        for (auto& kv : pending) outopt[kv.first] = kv.second;
+        // a bare token is an output file; the options gathered since the last -i / output belong to it. The first output is
+        // the Matroska file; RAWcooked's --framemd5 adds `[-an] -f framemd5 <file>` as a second one (Output.cpp:312-332)
+        if (outputs.empty()) {
+            for (auto& kv : pending) outopt[kv.first] = kv.second;
+        } else {
+            const auto f = pending.find("-f");
+            if (f == pending.end() || f->second != "framemd5" || !framemd5_path.empty())
+                return fail("only one Matroska output and one `-f framemd5` output are supported");
+            framemd5_path = a;
+        }
         pending.clear();
         outputs.push_back(a);
     }
     if (inputs.empty()) return fail("no input (-i)");
     if (outputs.empty()) return fail("no output file");
-    if (outputs.size() > 1) return fail("only one Matroska output is supported (framemd5 and extra outputs are not)");
     if (outopt.count("-f") && outopt["-f"] != "matroska") return fail("only -f matroska is supported");
     if (outopt.count("-c:v") && outopt["-c:v"] != "ffv1") return fail("only -c:v ffv1 is supported");
     if (outopt.count("-coder") && outopt["-coder"] != "1") return fail("only -coder 1 is supported");
@@ -459,6 +495,7 @@ extern "C" int b200enc_main(int argc, char** argv) {
             const auto r = in.opt.find("-r");
             v.fps = fr != in.opt.end() ? parse_rate(fr->second) : r != in.opt.end() ? parse_rate(r->second) : 25.0;   // ffmpeg's image2 default
             if (v.fps <= 0) v.fps = 25.0;
+            parse_rate_q(fr != in.opt.end() ? fr->second : r != in.opt.end() ? r->second : std::string("25"), &v.fps_num, &v.fps_den);
             order.push_back({'v', (int)videos.size()});
             videos.push_back(v);
         } else if (kind == 'w') {
@@ -562,7 +599,28 @@ extern "C" int b200enc_main(int argc, char** argv) {
     };
     for (size_t vi = 0; vi < videos.size(); vi++) {
         std::string verr;
-        const int rc = encode_video_stream(videos[vi], encs[vi], devices, frames_in_flight, nthreads, slices, context, slicecrc, mux, flush_audio_until, pc, &verr);
+        std::vector<uint8_t> md5s;
+        const bool want_md5 = vi == 0 && !framemd5_path.empty();        // a framemd5 output without -map takes the first video stream
+        if (want_md5) md5s.assign(16 * videos[vi].files.size(), 0);
+        const int rc = encode_video_stream(videos[vi], encs[vi], devices, frames_in_flight, nthreads, slices, context, slicecrc, mux, flush_audio_until, pc, &verr,
+                                           want_md5 ? &md5s : nullptr);
+        if (!rc && want_md5) {
+            // the file libavformat's framehash muxer writes (framehash.c ff_framehash_write_header, hashenc.c framehash_write_packet):
+            // one rawvideo stream, time base = 1 / frame rate, pts = frame index
+            const VideoStream& v = videos[vi];
+            FILE* f = fopen(framemd5_path.c_str(), "w");
+            if (!f) { cleanup(); return fail("cannot write " + framemd5_path, B200_ERR_IO); }
+            fprintf(f, "#format: frame checksums\n#version: 2\n#hash: MD5\n#software: b200enc %u.%u.%u\n", b200_version() >> 16, (b200_version() >> 8) & 255, b200_version() & 255);
+            fprintf(f, "#tb 0: %lld/%lld\n#media_type 0: video\n#codec_id 0: rawvideo\n#dimensions 0: %ux%u\n#sar 0: 0/1\n", v.fps_den, v.fps_num, v.info.width, v.info.height);
+            fprintf(f, "#stream#, dts,        pts, duration,     size, hash\n");
+            const size_t raw = b200_rawvideo_bytes(v.info.width, v.info.height, v.info.layout);
+            for (size_t i = 0; i < v.files.size(); i++) {
+                fprintf(f, "%d, %10lld, %10lld, %8lld, %8zu, ", 0, (long long)i, (long long)i, 1ll, raw);
+                for (int k = 0; k < 16; k++) fprintf(f, "%02x", md5s[16 * i + k]);
+                fputc('\n', f);
+            }
+            if (fclose(f)) { cleanup(); return fail("cannot write " + framemd5_path, B200_ERR_IO); }
+        }
         encs[vi] = nullptr;                    // closed by the workers
         if (rc) { cleanup(); return fail(verr, rc); }
     }

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "ffv1_host.h"
+#include "pixel_layouts.cuh"
 
 void b200_set_error(const std::string& msg);
 
@@ -226,6 +227,45 @@ __global__ void __launch_bounds__(256) k_padding_packed(const PadArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The frame as FFmpeg's rawvideo encoder emits it for the flavor (what a `-f framemd5` output hashes,
+// /root/reference/Source/CLI/Output.cpp:312-332): the pix_fmt of libavcodec's dpx / tiff decoder, planes back to back, rows
+// without padding. kind 0: rgb24, 1: rgb48 little endian, 2: rgb48 big endian, 3: gbrp 16-bit little endian (planes G, B, R)
+__global__ void __launch_bounds__(256) k_rawframe(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t frame_bytes,
+                                                  uint32_t row_bytes, size_t raw_bytes, int w, int h, int layout, int kind) {
+    const int f = blockIdx.y;
+    const uint8_t* fin = in + (size_t)f * frame_bytes;
+    uint8_t* fo = out + (size_t)f * raw_bytes;
+    const size_t npx = (size_t)w * h;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < npx; i += (size_t)gridDim.x * 256) {
+        const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+        int r, g, b;
+        b200::load_rgb(fin + (size_t)y * row_bytes, layout, x, r, g, b);
+        if (kind == 0) {
+            uint8_t* q = fo + 3 * i;
+            q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
+        } else if (kind == 3) {
+            uint16_t* q = reinterpret_cast<uint16_t*>(fo);
+            q[i] = (uint16_t)g; q[npx + i] = (uint16_t)b; q[2 * npx + i] = (uint16_t)r;
+        } else {
+            uint16_t* q = reinterpret_cast<uint16_t*>(fo) + 3 * i;
+            if (kind == 2) { r = (int)__byte_perm((uint32_t)r, 0, 0x4401); g = (int)__byte_perm((uint32_t)g, 0, 0x4401); b = (int)__byte_perm((uint32_t)b, 0, 0x4401); }
+            q[0] = (uint16_t)r; q[1] = (uint16_t)g; q[2] = (uint16_t)b;
+        }
+    }
+}
+
+int rawvideo_kind(int layout) {
+    switch (layout) {
+        case B200_DPX_RGB_8: case B200_TIFF_RGB_8: return 0;
+        case B200_DPX_RGB_16_LE: case B200_TIFF_RGB_16_LE: return 1;
+        case B200_DPX_RGB_16_BE: case B200_TIFF_RGB_16_BE: return 2;
+        case B200_DPX_RGB_10_FILLED_A_LE: case B200_DPX_RGB_10_FILLED_A_BE:
+        case B200_DPX_RGB_12_FILLED_A_LE: case B200_DPX_RGB_12_FILLED_A_BE: case B200_DPX_RGB_12_PACKED_BE: return 3;
+    }
+    return -1;
+}
+
 }  // namespace
 
 struct b200_scan {
@@ -234,6 +274,7 @@ struct b200_scan {
     size_t max_bytes = 0;
     uint8_t* d_data = nullptr;
     uint8_t* d_out = nullptr;            // masked payloads of the host entry point (allocated on first use)
+    uint8_t* d_raw = nullptr; size_t raw_cap = 0;   // rawvideo frames of the framemd5 entry points (allocated on first use)
     uint64_t *d_off = nullptr, *d_len = nullptr;
     uint32_t* d_dig = nullptr;
     unsigned long long *d_cnt = nullptr, *d_first = nullptr;
@@ -282,7 +323,7 @@ void b200_scan_close(b200_scan* S) {
     cudaSetDevice(S->device);
     if (S->stream) { cudaStreamSynchronize(S->stream); cudaStreamDestroy(S->stream); }
     for (auto v : S->ev) if (v) cudaEventDestroy(v);
-    for (void* p : {(void*)S->d_data, (void*)S->d_out, (void*)S->d_off, (void*)S->d_len, (void*)S->d_dig, (void*)S->d_cnt, (void*)S->d_first})
+    for (void* p : {(void*)S->d_data, (void*)S->d_out, (void*)S->d_raw, (void*)S->d_off, (void*)S->d_len, (void*)S->d_dig, (void*)S->d_cnt, (void*)S->d_first})
         if (p) cudaFree(p);
     for (void* p : {(void*)S->h_meta, (void*)S->h_dig, (void*)S->h_res}) if (p) cudaFreeHost(p);
     delete S;
@@ -415,6 +456,66 @@ int b200_padding_host(b200_scan* S, uint32_t width, uint32_t height, int32_t lay
         SCU(cudaStreamSynchronize(S->stream));
     }
     return 0;
+}
+
+size_t b200_rawvideo_bytes(uint32_t width, uint32_t height, int32_t layout) {
+    const int k = rawvideo_kind(layout);
+    return k < 0 ? 0 : (size_t)width * height * (k == 0 ? 3 : 6);
+}
+
+const char* b200_rawvideo_pix_fmt(int32_t layout) {
+    switch (rawvideo_kind(layout)) {
+        case 0: return "rgb24";
+        case 1: return "rgb48le";
+        case 2: return "rgb48be";
+        case 3: return b200::layout_bits(layout) == 10 ? "gbrp10le" : "gbrp12le";
+    }
+    return "";
+}
+
+int b200_framemd5_device(b200_scan* S, uint32_t width, uint32_t height, int32_t layout, const void* d_payloads, int32_t n,
+                         uint8_t* digests, void* stream) {
+    if (!S || !d_payloads || !digests) return sfail(B200_ERR_INVALID, "null argument");
+    if (n < 1 || n > S->max_items) return sfail(B200_ERR_INVALID, "n out of range");
+    const int kind = rawvideo_kind(layout);
+    if (kind < 0 || !width || !height) return sfail(B200_ERR_INVALID, "unsupported layout");
+    SCU(cudaSetDevice(S->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t rb = (uint32_t)b200::layout_row_bytes(width, layout);
+    const size_t fb = (size_t)rb * height, raw = b200_rawvideo_bytes(width, height, layout);
+    std::vector<size_t> off(n), len(n, raw);
+    // flavors whose payload already is the raw frame (tight rows of rgb24 / rgb48 in the file's byte order) are hashed in place
+    const bool in_place = kind != 3 && fb == raw;
+    if (in_place) {
+        for (int i = 0; i < n; i++) off[i] = (size_t)i * fb;
+        return b200_md5_device(S, d_payloads, off.data(), len.data(), n, digests, stream);
+    }
+    const size_t stride = (raw + 15) & ~(size_t)15;
+    if (stride * n > S->raw_cap) {
+        if (S->d_raw) cudaFree(S->d_raw);
+        S->d_raw = nullptr; S->raw_cap = 0;
+        SCU(cudaMalloc(reinterpret_cast<void**>(&S->d_raw), stride * (size_t)S->max_items + 64));
+        S->raw_cap = stride * (size_t)S->max_items;
+    }
+    const size_t npx = (size_t)width * height;
+    unsigned gx = (unsigned)((npx + 256 * 4 - 1) / (256 * 4));
+    if (gx > 148 * 4) gx = 148 * 4;
+    k_rawframe<<<dim3(gx, n), 256, 0, s>>>(static_cast<const uint8_t*>(d_payloads), S->d_raw, fb, rb, stride, (int)width, (int)height, layout, kind);
+    SCU(cudaGetLastError());
+    for (int i = 0; i < n; i++) off[i] = (size_t)i * stride;
+    return b200_md5_device(S, S->d_raw, off.data(), len.data(), n, digests, stream);
+}
+
+int b200_framemd5_host(b200_scan* S, uint32_t width, uint32_t height, int32_t layout, const uint8_t* const* payloads, int32_t n,
+                       uint8_t* digests) {
+    if (!S || !payloads || !digests) return sfail(B200_ERR_INVALID, "null argument");
+    if (n < 1 || n > S->max_items) return sfail(B200_ERR_INVALID, "n out of range");
+    SCU(cudaSetDevice(S->device));
+    const size_t fb = b200::layout_row_bytes(width, layout) * (size_t)height;
+    if (!fb) return sfail(B200_ERR_INVALID, "unsupported layout");
+    if (fb * n > S->max_bytes) return sfail(B200_ERR_OVERFLOW, "more bytes than the handle was opened for");
+    for (int i = 0; i < n; i++) SCU(cudaMemcpyAsync(S->d_data + (size_t)i * fb, payloads[i], fb, cudaMemcpyHostToDevice, S->stream));
+    return b200_framemd5_device(S, width, height, layout, S->d_data, n, digests, S->stream);
 }
 
 int b200_scan_stats(const b200_scan* S, uint64_t stats[4]) {

@@ -25,8 +25,22 @@ def _lib():
         L.b200_padding_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_void_p, C.c_int32,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
         L.b200_scan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.b200_rawvideo_bytes.restype = C.c_size_t
+        L.b200_rawvideo_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_int32]
+        L.b200_rawvideo_pix_fmt.restype = C.c_char_p
+        L.b200_rawvideo_pix_fmt.argtypes = [C.c_int32]
+        L.b200_framemd5_host.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]
+        L.b200_framemd5_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _bound = True
     return L
+
+
+def rawvideo_bytes(width, height, layout):
+    return _lib().b200_rawvideo_bytes(width, height, layout)
+
+
+def rawvideo_pix_fmt(layout):
+    return _lib().b200_rawvideo_pix_fmt(layout).decode()
 
 
 class Scanner:
@@ -78,6 +92,15 @@ class Scanner:
         first = (C.c_uint64 * n)()
         _enc._check(self._L.b200_padding_device(self._h, width, height, layout, d_payloads, n, cnt, first, d_masked, stream))
         return list(cnt), [None if f == NONE else int(f) for f in first]
+
+    def framemd5(self, width, height, layout, payloads):
+        """MD5 of every frame as a `-f framemd5` output hashes it (FFmpeg's rawvideo form of the flavor)."""
+        n = len(payloads)
+        keep = [np.frombuffer(b, np.uint8) if not isinstance(b, np.ndarray) else np.ascontiguousarray(b, np.uint8) for b in payloads]
+        ptrs = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+        out = C.create_string_buffer(16 * n)
+        _enc._check(self._L.b200_framemd5_host(self._h, width, height, layout, ptrs, n, out))
+        return [out.raw[16 * i:16 * i + 16] for i in range(n)]
 
     def stats(self):
         s = (C.c_uint64 * 4)()

@@ -221,3 +221,23 @@ def test_rawcooked_output_version_2(tmp_path):
     victim.write_bytes(bytes(b))
     code2, out2 = run_rawcooked(["--check", name + ".mkv", "-o", "./"], cwd=str(tmp_path))
     assert OK not in out2 and ("not same" in out2 or code2 != 0), out2
+
+
+def test_framemd5_second_output(tmp_path):
+    # `rawcooked --framemd5` adds `-f framemd5 <dir>.framemd5` to the command line (Output.cpp:312-332); the file must equal
+    # what FFmpeg's own libraries write for the same frames (tests/golden/framemd5_golden.json), but for the #software line
+    import json
+    cases = json.load(open(os.path.join(util.ROOT, "tests", "golden", "framemd5_golden.json")))["cases"]
+    c = [k for k in cases if k["layout"] == S.DPX_RGB_10_FA_BE][0]
+    name = "md5seq"
+    d = tmp_path / name
+    os.makedirs(d)
+    for i in range(c["frames"]):
+        payload = S.synth_payload(c["w"], c["h"], c["layout"], c["seed"] + i)
+        open(d / ("f_%06d.dpx" % i), "wb").write(S.dpx_file(c["w"], c["h"], c["layout"], payload, i))
+    code, out = run_rawcooked(["--framemd5", "-framerate", "30000/1001", "--check", "-y", "-b", B200ENC, "-slices", "4", name], cwd=str(tmp_path))
+    assert code == 0, out
+    assert OK in out, out
+    got = (tmp_path / (name + ".framemd5")).read_text()
+    strip = lambda t: "\n".join(l for l in t.splitlines() if not l.startswith("#software:"))
+    assert strip(got) == strip(c["text"]), got

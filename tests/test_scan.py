@@ -131,3 +131,52 @@ def test_cuda_padding_test_equals_oracle(layout, w, h):
         assert (cnt2, first2) == (cnt, first)
     finally:
         sc.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# framemd5 (the second output of RAWcooked's --framemd5, Output.cpp:312-332)
+def _framemd5_golden():
+    import json
+    return json.load(open(os.path.join(util.ROOT, "tests", "golden", "framemd5_golden.json")))["cases"]
+
+
+def _without_software(text):
+    return "\n".join(l for l in text.splitlines() if not l.startswith("#software:")) + "\n"
+
+
+def test_framemd5_oracle_equals_ffmpeg_golden():
+    # the numpy restatement (pix_fmt per flavor, plane order, text layout) against the files FFmpeg's own libavcodec decoders
+    # + libavformat framemd5 muxer produced (tests/golden/make_framemd5_golden.py)
+    for c in _framemd5_golden():
+        w, h, layout = c["w"], c["h"], c["layout"]
+        assert scan_oracle.PIX_FMT[layout] == c["pix_fmt"]
+        rows = []
+        for i in range(c["frames"]):
+            raw = scan_oracle.rawvideo_frame(S.synth_payload(w, h, layout, c["seed"] + i), w, h, layout)
+            rows.append((len(raw), hashlib.md5(raw).digest()))
+        assert scan_oracle.framemd5_text(w, h, c["fps_num"], c["fps_den"], rows) == _without_software(c["text"]), (w, h, layout)
+
+
+@pytest.mark.gpu
+def test_cuda_framemd5_equals_ffmpeg_golden_and_oracle():
+    from rawcooked_b200 import scan
+    for c in _framemd5_golden():
+        w, h, layout, n = c["w"], c["h"], c["layout"], c["frames"]
+        payloads = [S.synth_payload(w, h, layout, c["seed"] + i) for i in range(n)]
+        sc = scan.Scanner(max_items=n, max_bytes=n * S.frame_bytes(w, h, layout))
+        try:
+            digs = sc.framemd5(w, h, layout, payloads)
+            assert scan.rawvideo_pix_fmt(layout) == c["pix_fmt"]
+            size = scan.rawvideo_bytes(w, h, layout)
+            assert scan_oracle.framemd5_text(w, h, c["fps_num"], c["fps_den"], [(size, d) for d in digs]) == _without_software(c["text"])
+        finally:
+            sc.close()
+    # a larger frame of every layout against the oracle
+    for layout in sorted(S.LAYOUT_BITS):
+        w, h = 333, 41
+        payloads = [S.synth_payload(w, h, layout, 700 + i) for i in range(3)]
+        sc = scan.Scanner(max_items=3, max_bytes=3 * S.frame_bytes(w, h, layout))
+        try:
+            assert sc.framemd5(w, h, layout, payloads) == [hashlib.md5(scan_oracle.rawvideo_frame(p, w, h, layout)).digest() for p in payloads]
+        finally:
+            sc.close()
