@@ -43,7 +43,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 traffic = {}
-for k in ("k_model", "k_range", "k_emit", "k_pack", "k_flac", "k_decode"):
+for k in ("k_model", "k_range", "k_emit", "k_pack", "k_flac", "k_decode", "k_md5", "k_padding"):
     rep = os.path.join(G, "%s_%s.ncu-rep" % (tag, k))
     if not os.path.exists(rep):
         continue

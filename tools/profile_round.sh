@@ -22,6 +22,10 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_fl
     python bench.py --config 4 --steps 1 --warmup 1 --no-cpu --no-check --no-decode > gpurun_out/${TAG}_ncu_k_flac.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_decode -c 1 -o gpurun_out/${TAG}_k_decode -f \
     python bench.py --frames 32 --steps 1 --warmup 1 --no-cpu --no-check > gpurun_out/${TAG}_ncu_k_decode.log 2>&1
+for K in k_md5 k_padding; do
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -o gpurun_out/${TAG}_$K -f \
+      python bench.py --config 2 --frames 64 --steps 1 --warmup 1 --no-cpu --no-check > gpurun_out/${TAG}_ncu_$K.log 2>&1
+done
 tail -3 gpurun_out/${TAG}_gpu_tests.log
 for f in gpurun_out/${TAG}_bench*.json; do echo $f; cut -c1-300 $f; done
 ls -la gpurun_out/${TAG}_*
