@@ -95,7 +95,7 @@ int b200_ffv1_dec_open(const b200_ffv1_dec_cfg* cfg, const uint8_t* record, size
     cudaError_t de = cudaGetDeviceCount(&ndev);
     if (de != cudaSuccess || ndev == 0) { delete D; return dfail(B200_ERR_NO_DEVICE, "no CUDA device: the B200 decoder has no CPU fallback"); }
     if (cfg->device < 0 || cfg->device >= ndev) { delete D; return dfail(B200_ERR_INVALID, "bad device ordinal"); }
-    DCU(cudaSetDevice(cfg->device));
+    { cudaError_t e_ = cudaSetDevice(cfg->device); if (e_ != cudaSuccess) { delete D; return dfail_cuda(e_, "cudaSetDevice"); } }
 
     const int B = cfg->max_frames;
     D->max_frames = B;

@@ -36,11 +36,15 @@ out = os.path.join(d, "out.mkv")
 cmd = [os.path.join(ROOT, "rawcooked_b200", "b200enc"), "-xerror", "-framerate", "24", "-r", "24", "-f", "image2", "-c:v", "dpx", "-start_number", "000000",
        "-i", os.path.join(d, "f_%06d.dpx"), "-c:a", "flac", "-c:v", "ffv1", "-coder", "1", "-context", "1", "-f", "matroska", "-g", "1", "-level", "3",
        "-slicecrc", "1", "-slices", "24", "-y", "-f", "matroska", out]
-for it in range(2):
+# plain, then with the encode-time verification (every packet decoded again on the GPU), then with a framemd5 second output
+variants = [("plain", {}, []), ("plain", {}, [])]
+if len(sys.argv) > 2:
+    variants += [("B200_VERIFY=1", {"B200_VERIFY": "1"}, []), ("-f framemd5", {}, ["-f", "framemd5", os.path.join(d, "out.framemd5")])]
+for it, (label, env, extra) in enumerate(variants):
     t = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, B200_CLI_TIMING='1'))
+    r = subprocess.run(cmd + extra, capture_output=True, text=True, env=dict(os.environ, B200_CLI_TIMING='1', **env))
     dt = time.perf_counter() - t
-    print("run %d: rc=%d %.2f s  %.1f fps  %.0f MPix/s  (process start + encoder open included)  mkv %.1f MB %s" %
-          (it, r.returncode, dt, n / dt, n * w * h / dt / 1e6, os.path.getsize(out) / 1e6 if os.path.exists(out) else 0, '\n' + r.stderr[-1500:]))
+    print("run %d (%s): rc=%d %.2f s  %.1f fps  %.0f MPix/s  (process start + encoder open included)  mkv %.1f MB %s" %
+          (it, label, r.returncode, dt, n / dt, n * w * h / dt / 1e6, os.path.getsize(out) / 1e6 if os.path.exists(out) else 0, '\n' + r.stderr[-700:]))
 for f in os.listdir(d):
     os.remove(os.path.join(d, f))
