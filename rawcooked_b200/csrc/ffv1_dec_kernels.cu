@@ -5,10 +5,11 @@
 // of the batch is decoded by ONE lane, `spw` slices share a warp (their lanes step through their streams sample by sample in
 // lockstep, so the warp issues one instruction stream for spw slices), and a finished row of any of them is turned into
 // file bytes by all 32 lanes (inverse RCT, byte layout, store and/or compare with the source payload).
-// Measured (B200, 4K 16-bit grain, 24 slices): a lane needs ~3 200 cycles per sample (~700 dependent instructions, one
+// Measured (B200, 4K 16-bit grain, 24 slices): a lane needs ~3 200 cycles per sample (~680 dependent instructions, one
 // every ~4.6 cycles: the chain of (low, range) through ~17 bins, plus one random 32-byte read of the context's states that no
 // cache holds, because the quantised context of noisy 16-bit material is spread over all 10 126 rows); throughput therefore
-// comes from warps in flight: 57 fps at 128 frames in flight (2 slices per warp), 97 fps at 256 (4 per warp).
+// comes from warps in flight: 58 fps at 128 frames in flight (2 slices per warp), 104 fps at 256 (4 per warp). Capping the
+// registers for more resident warps spills the coder state and loses (80 registers: 36 fps), hence B200_DEC_MIN_CTAS = 4.
 //
 //   packet -> slices (tail walk)        /root/reference/Source/Lib/CoDec/FFV1/FFV1_Frame.cpp:166-197        k_dec_index
 //   slice CRC, keyframe bin, header     FFV1_Slice.cpp:210-260, :113-177                                     k_decode
