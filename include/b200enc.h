@@ -112,6 +112,12 @@ int b200_ffv1_encode_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int3
  * allocated when first needed). A third submit without a fetch gives up the oldest batch. Do not mix with
  * b200_ffv1_encode_device while host batches are in flight. */
 int b200_ffv1_submit_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int32_t n_frames);
+/* Optional, ahead of a submit: starts the host->device copy of the NEXT batch (whole frames, into the staging buffer the batch
+ * in flight does not use) and returns at once. Called before the fetch of the previous batch,
+ *     submit(0); submit(1); prefetch(2); fetch -> 0; submit(2); prefetch(3); fetch -> 1; submit(3); ...
+ * the upload of batch i+1 and the download of batch i-1 share the PCIe link in both directions while batch i is coded; the
+ * following b200_ffv1_submit_host with the same frames then only launches kernels. Without a batch in flight it does nothing. */
+int b200_ffv1_prefetch_host(b200_ffv1_enc* enc, const uint8_t* const* frames, int32_t n_frames);
 
 /* Device-resident variant: `d_frames` is ONE device buffer holding n_frames payloads back to back
  * (stride b200_ffv1_frame_bytes()); packets are produced into an internal device buffer.

@@ -57,6 +57,11 @@ struct b200_ffv1_enc {
     int max_frames = 0;
     std::vector<void*> owned;       // device allocations
     uint8_t* d_in = nullptr;        // staging for the host entry point (allocated on first use)
+    uint8_t* d_in2 = nullptr;       // second staging buffer: the frames of the next batch cross PCIe while this one is coded
+    cudaEvent_t ev_prefetch = nullptr;
+    int prefetched_set = -1;        // b200_ffv1_prefetch_host has put a batch into this staging buffer (-1: none)
+    const uint8_t* prefetched_first = nullptr;
+    int prefetched_n = 0;
     size_t max_packet = 0;
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -324,7 +329,7 @@ int b200_ffv1_open(const b200_ffv1_cfg* cfg, b200_ffv1_enc** out) {
     cudaStreamCreateWithFlags(&E->sc, cudaStreamNonBlocking);
     E->ev_h2d.resize(A.nbands);
     for (auto& ev : E->ev_h2d) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    for (cudaEvent_t* ev : {&E->ev_start, &E->ev_done_m, &E->ev_done_e}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    for (cudaEvent_t* ev : {&E->ev_start, &E->ev_done_m, &E->ev_done_e, &E->ev_prefetch}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     for (int pz = 0; pz < b200_ffv1_enc::kPar; pz++)
         for (cudaEvent_t* ev : {&E->ev_model[pz], &E->ev_range[pz], &E->ev_emit[pz]}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     {
@@ -354,6 +359,8 @@ void b200_ffv1_close(b200_ffv1_enc* E) {
     cudaDeviceSynchronize();
     for (void* p : E->owned) cudaFree(p);
     if (E->d_in) cudaFree(E->d_in);
+    if (E->d_in2) cudaFree(E->d_in2);
+    if (E->ev_prefetch) cudaEventDestroy(E->ev_prefetch);
     for (auto& R : E->rs) {
         if (R.h_flags) cudaFreeHost(R.h_flags);
         if (R.done) cudaEventDestroy(R.done);
@@ -405,7 +412,22 @@ int b200_ffv1_set_timing(b200_ffv1_enc* E, int32_t enabled) {
 
 // host_frames != nullptr: the payloads are still in host memory; they are copied to d_frames band by band on the copy stream,
 // each band's rows just ahead of the k_model launch that needs them, so that the transfer hides behind the kernels
-static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, cudaStream_t s, const uint8_t* const* host_frames, int set) {
+// whole frames of a batch into a staging buffer, on the copy stream, behind the last kernels that read that buffer
+static int prefetch_copies(b200_ffv1_enc* E, uint8_t* d_buf, const uint8_t* const* host_frames, int32_t n_frames, int set) {
+    // the buffer was last read by the batch that used this result set: its `done` event covers every kernel of it
+    CU(cudaStreamWaitEvent(E->sc, E->rs[set].done, 0));
+    for (int i = 0; i < n_frames; i++)
+        CU(cudaMemcpyAsync(d_buf + (size_t)i * E->st.frame_bytes, host_frames[i], E->st.frame_bytes, cudaMemcpyHostToDevice, E->sc));
+    CU(cudaEventRecord(E->ev_prefetch, E->sc));
+    return 0;
+}
+
+// prefetch (a batch is already in flight): the frames go to the staging buffer whole and at once, on the copy stream, while
+// the batch ahead is still being coded from the other staging buffer; the first k_model launch waits for all of them. Large
+// copies run at the full PCIe rate (the band-sized pieces of 368 KB reach ~16 GB/s next to the packet download, which made
+// the end-to-end path transfer-bound on 4K 16-bit), and nothing of the transfer is left between two batches.
+static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames, cudaStream_t s, const uint8_t* const* host_frames, int set,
+                       bool prefetch = false) {
     CU(cudaSetDevice(E->cfg.device));
     b200_ffv1_enc::ResultSet& R = E->rs[set];
     if (!R.arena) {     // second result set, first use
@@ -468,7 +490,15 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
     if (host_frames) {
         for (const auto& g : E->st.slices)
             if (srows.empty() || srows.back().first != g.y0) srows.push_back({g.y0, g.h});
-        if (!serial) { CU(cudaEventRecord(E->ev_start, s)); CU(cudaStreamWaitEvent(E->sc, E->ev_start, 0)); }
+        if (serial) prefetch = false;
+        if (prefetch) {
+            if (!(E->prefetched_set == set && E->prefetched_first == host_frames[0] && E->prefetched_n == n_frames)) {
+                int r = prefetch_copies(E, (uint8_t*)d_frames, host_frames, n_frames, set);
+                if (r) return r;
+            }
+            E->prefetched_set = -1;
+            CU(cudaStreamWaitEvent(sm, E->ev_prefetch, 0));
+        } else if (!serial) { CU(cudaEventRecord(E->ev_start, s)); CU(cudaStreamWaitEvent(E->sc, E->ev_start, 0)); }
     }
     // emit(band): after range(band); frees the band buffers of its set for model(band + kpar)
     auto do_emit = [&](int band) -> int {
@@ -484,7 +514,7 @@ static int encode_impl(b200_ffv1_enc* E, const void* d_frames, int32_t n_frames,
     };
     for (int band = 0; band < nb; band++) {
         const int p = band % E->kpar;
-        if (host_frames) {
+        if (host_frames && !prefetch) {
             cudaStream_t sc = serial ? s : E->sc;
             const size_t rb = E->st.row_bytes;
             for (int i = 0; i < n_frames; i++)
@@ -644,12 +674,28 @@ int b200_ffv1_packet_sizes(b200_ffv1_enc* E, size_t* out_off, size_t* out_len, i
     return 0;
 }
 
+int b200_ffv1_prefetch_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames) {
+    if (!E || !frames) return fail(B200_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
+    CU(cudaSetDevice(E->cfg.device));
+    for (int i = 0; i < n_frames; i++)
+        if (!frames[i]) return fail(B200_ERR_INVALID, "null frame pointer");
+    if (!E->host_mode || E->fifo_n == 0 || E->timing) return 0;         // nothing in flight: the submit copies band by band
+    // the staging buffer (= result set) the next submit will take: the one the newest batch in flight does not use
+    const int set = E->fifo[E->fifo_n - 1] ^ 1;
+    uint8_t** buf = set ? &E->d_in2 : &E->d_in;
+    if (!*buf) CU(cudaMalloc((void**)buf, E->st.frame_bytes * E->max_frames));
+    int r = prefetch_copies(E, *buf, frames, n_frames, set);
+    if (r) return r;
+    E->prefetched_set = set; E->prefetched_first = frames[0]; E->prefetched_n = n_frames;
+    return 0;
+}
+
 int b200_ffv1_submit_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames) {
     if (!E || !frames) return fail(B200_ERR_INVALID, "null argument");
     if (n_frames < 1 || n_frames > E->max_frames) return fail(B200_ERR_INVALID, "n_frames out of range");
     CU(cudaSetDevice(E->cfg.device));
     const size_t fb = E->st.frame_bytes;
-    if (!E->d_in) CU(cudaMalloc((void**)&E->d_in, fb * E->max_frames));
     for (int i = 0; i < n_frames; i++)
         if (!frames[i]) return fail(B200_ERR_INVALID, "null frame pointer");
     // result set: 0 when nothing is in flight; the free one when one batch is; with two in flight the oldest is given up
@@ -657,8 +703,12 @@ int b200_ffv1_submit_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_
     int set = 0;
     if (E->fifo_n == 1) set = E->fifo[0] ^ 1;
     else if (E->fifo_n == 2) { set = E->fifo[0]; E->fifo[0] = E->fifo[1]; E->fifo_n = 1; }
+    // one staging buffer per result set; with a batch in flight the new one is prefetched into the other buffer
+    const bool prefetch = E->fifo_n >= 1 && !E->timing && !getenv("B200_NO_PREFETCH");
     E->fifo[E->fifo_n++] = set;
-    return encode_impl(E, E->d_in, n_frames, E->sh, frames, set);
+    uint8_t** buf = set ? &E->d_in2 : &E->d_in;
+    if (!*buf) CU(cudaMalloc((void**)buf, fb * E->max_frames));
+    return encode_impl(E, *buf, n_frames, E->sh, frames, set, prefetch);
 }
 
 int b200_ffv1_encode_host(b200_ffv1_enc* E, const uint8_t* const* frames, int32_t n_frames,

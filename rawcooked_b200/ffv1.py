@@ -49,6 +49,7 @@ def load_library():
     L.b200_ffv1_encode_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t,
                                         C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.b200_ffv1_submit_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
+    L.b200_ffv1_prefetch_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
     L.b200_ffv1_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.b200_ffv1_packets_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32]
     L.b200_ffv1_fetch_packets.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int32]
@@ -149,6 +150,14 @@ class FFV1Encoder:
         ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
         self._inflight = getattr(self, "_inflight", [])[-1:] + [(arrs, ptrs)]
         _check(self._L.b200_ffv1_submit_host(self._h, ptrs, n))
+
+    def prefetch(self, frames):
+        """Starts the upload of the batch the NEXT submit will take (call it before fetching the previous batch's packets)."""
+        n = len(frames)
+        arrs = [np.ascontiguousarray(np.frombuffer(f, np.uint8) if not isinstance(f, np.ndarray) else f, dtype=np.uint8) for f in frames]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        self._prefetched = (arrs, ptrs)
+        _check(self._L.b200_ffv1_prefetch_host(self._h, ptrs, n))
 
     def encode_device(self, d_ptr, n_frames, stream=0):
         """Asynchronous device-resident encode: d_ptr = device address of n_frames payloads back to back."""

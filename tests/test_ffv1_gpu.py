@@ -151,6 +151,29 @@ def test_two_host_batches_in_flight():
         enc.close()
 
 
+def test_prefetch_ahead_of_the_fetch():
+    # b200_ffv1_prefetch_host: the upload of batch i+1 starts before the packets of batch i-1 are fetched; the following submit
+    # only launches kernels. Also: a prefetch that the submit does not match (other frames) is ignored, not used
+    w, h, layout, slices = 200, 150, S.DPX_RGB_16_BE, 6
+    enc = ffv1.FFV1Encoder(w, h, layout, slices=slices, max_frames=3)
+    try:
+        nh, nv = enc.grid
+        batches = [[S.synth_payload(w, h, layout, 800 + 10 * b + k, "grain" if (b + k) % 2 else "white") for k in range(3 - (b % 2))] for b in range(6)]
+        want = [[util.oracle_encode(f, w, h, layout, nh, nv) for f in bt] for bt in batches]
+        enc.prefetch(batches[0])                     # nothing in flight: does nothing
+        enc.submit(batches[0])
+        enc.submit(batches[1])
+        for b in range(2, 6):
+            enc.prefetch(batches[b] if b != 4 else batches[0])      # batch 4: a prefetch of the wrong frames
+            assert [p.tobytes() for p in enc.fetch_packets(len(batches[b - 2]))] == want[b - 2]
+            enc.submit(batches[b])
+        assert [p.tobytes() for p in enc.fetch_packets(len(batches[4]))] == want[4]
+        assert [p.tobytes() for p in enc.fetch_packets(len(batches[5]))] == want[5]
+        assert enc.encode(batches[2]) == want[2]
+    finally:
+        enc.close()
+
+
 def test_device_resident_entry_point():
     import torch
     w, h, layout, slices = 320, 240, S.DPX_RGB_16_BE, 4
