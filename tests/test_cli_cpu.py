@@ -54,3 +54,27 @@ def test_video_needs_a_device(tmp_path):
         open(d / ("f_%06d.dpx" % i), "wb").write(S.dpx_file(64, 48, S.DPX_RGB_16_BE, S.synth_payload(64, 48, S.DPX_RGB_16_BE, i), i))
     code, out = run_rawcooked(["--check", "-y", "-b", B200ENC, name], cwd=str(tmp_path))
     assert code != 0 and "no CUDA device" in out and OK not in out, out
+
+
+@needs
+def test_output_grammar_of_the_front_end(tmp_path):
+    # what follows the Matroska output on the command line (Output.cpp:306-332): one `-f framemd5 <file>` is accepted, anything
+    # else is refused with a message and a non-zero status, before any device is touched
+    wav = tmp_path / "a.wav"
+    wav.write_bytes(S.wav_file(S.wav_pcm(2, 48000, 16, 4800, 5), 48000, 16))
+    base = [B200ENC, "-xerror", "-i", str(wav), "-c:a", "copy", "-c:v", "ffv1", "-coder", "1", "-context", "1", "-f", "matroska", "-g", "1",
+            "-level", "3", "-slicecrc", "1", "-y", "-f", "matroska", str(tmp_path / "o.mkv")]
+    p = subprocess.run(base + ["-an", "-f", "framemd5", str(tmp_path / "o.framemd5")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr                                    # audio only: nothing to hash, the MKV is written
+    assert (tmp_path / "o.mkv").read_bytes()[:4] == b"\x1a\x45\xdf\xa3"
+    p = subprocess.run(base + ["-f", "md5", str(tmp_path / "o.md5")], capture_output=True, text=True, timeout=60)
+    assert p.returncode != 0 and "framemd5" in p.stderr
+    p = subprocess.run(base + ["-f", "framemd5", str(tmp_path / "1.framemd5"), "-f", "framemd5", str(tmp_path / "2.framemd5")],
+                       capture_output=True, text=True, timeout=60)
+    assert p.returncode != 0
+    # -n with an existing output: refuse like ffmpeg does (Output.cpp:85-87)
+    p = subprocess.run([a if a != "-y" else "-n" for a in base], capture_output=True, text=True, timeout=60)
+    assert p.returncode != 0 and "already exists" in p.stderr
+    # option values RAWcooked never emits are refused, not ignored
+    p = subprocess.run([a if a != "1" or i != base.index("-coder") + 1 else "0" for i, a in enumerate(base)], capture_output=True, text=True, timeout=60)
+    assert p.returncode != 0 and "-coder" in p.stderr
