@@ -120,3 +120,26 @@ def test_decoder_needs_a_device():
     with pytest.raises(ffv1.B200Error) as e:
         ffv1dec.FFV1Decoder(w, h, layout, rec)
     assert e.value.code == -2
+
+
+def test_config_record_round_trip_over_the_option_space():
+    # host range encoder (ffv1_host.cpp) against host range decoder (ffv1_dec_host.cpp) over layouts x grids x context x ec:
+    # what the encoder's record says must be what the decoder's parser reads
+    from rawcooked_b200 import ffv1dec
+    n = 0
+    for layout in sorted(S.LAYOUT_BITS):
+        for (w, h) in ((64, 48), (1920, 1080), (4096, 3112), (131, 77)):
+            for slices in (4, 6, 9, 12, 16, 24, 30, 64, 576):
+                try:
+                    nh, nv = ffv1.slice_grid(w, h, slices)
+                except ffv1.B200Error:
+                    continue
+                if nh >= w or nv >= h:
+                    continue
+                for context in (0, 1):
+                    for ec in (0, 1):
+                        rec = ffv1.config_record(w, h, layout, slices=slices, context=context, slicecrc=ec)
+                        p = ffv1dec.parse_config_record(rec)
+                        assert (p.num_h_slices, p.num_v_slices, p.ec, p.bits_per_raw_sample, p.crc_ok) == (nh, nv, ec, S.LAYOUT_BITS[layout], 1)
+                        n += 1
+    assert n > 500
