@@ -20,7 +20,7 @@
  *   CRC                    ZenCRC32                      Source/Lib/Utils/CRC32/ZenCRC32.cpp:1097-1135
  *   pixel layouts + RCT    Transform                     Source/Lib/Transform/Transform.cpp:29-37, :70-420
  *
- * Pinning (tests/test_oracle.py): (1) every packet decodes through the UNMODIFIED reference decoder
+* Pinning of the encoder half (tests/test_oracle.py): (1) every packet decodes through the UNMODIFIED reference decoder
  * (oracle/_ref/libref_ffv1dec.so) to the input bytes — the property all of the reference's own tests pin
  * (test1.sh, test2.sh, slices.sh: round trip through `rawcooked --check`); (2) config record and packets
  * are byte-identical to libavcodec 62.11.100's for the golden vectors in tests/golden/.
@@ -497,4 +497,261 @@ size_t ffv1o_slice_bins(const ffv1o_cfg* cfg, const uint8_t* payload, int sx, in
     encode_slice(cfg, payload, sx, sy, sx == 0 && sy == 0, buf, bufcap, dump_hook, &d, NULL, &overflow);
     free(buf);
     return d.n;
+}
+
+/* =====================================================================================================
+ * Decoder restatement (the `--check` side): plain C, one slice after the other, following
+ *   record            parameters::Parse            Source/Lib/CoDec/FFV1/FFV1_Parameters.cpp:23-253
+ *   packet -> slices  ffv1_frame::Process          Source/Lib/CoDec/FFV1/FFV1_Frame.cpp:134-228
+ *   slice             slice::Parse / SliceHeader   Source/Lib/CoDec/FFV1/FFV1_Slice.cpp:113-177, :210-318
+ *   rows              SliceContent_LineThenPlane   FFV1_Slice.cpp:406-444, Line :447-472, predict / context :21-93
+ *   range decoder     rangecoder::b / u / s        Source/Lib/CoDec/FFV1/FFV1_RangeCoder.cpp:25-171
+ *   pixels            JPEG2000RCT + byte layouts   Source/Lib/Transform/Transform.cpp:29-37, :70-420
+ * Pinned (tests/test_oracle.py): its output equals the UNMODIFIED reference decoder's (oracle/_ref) and the source payload
+ * on every golden packet of libavcodec and on the encoder restatement's packets of every layout.
+ * ===================================================================================================== */
+typedef struct {
+    const uint8_t* beg; size_t cur, end;      /* Buffer_Cur / Buffer_End as offsets */
+    uint32_t low, range;                      /* Current / Mask */
+    uint8_t one[256], zero[256];
+    int underrun;
+} rdec;
+
+static void rdec_init(rdec* d, const uint8_t* buf, size_t size, const uint8_t one[256])
+{
+    d->beg = buf; d->cur = 0; d->end = size;
+    d->low = size ? buf[0] : 0;               /* AssignBuffer, FFV1_RangeCoder.cpp:22-34 */
+    d->range = 0xFF;
+    d->cur = 1;
+    d->underrun = 0;
+    memcpy(d->one, one, 256);
+    make_zero_state(d->one, d->zero);
+}
+
+static int rdec_bin(rdec* d, uint8_t* state)   /* rangecoder::b, FFV1_RangeCoder.cpp:71-102 */
+{
+    if (d->range < 0x100) {
+        d->low <<= 8;
+        if (d->cur > d->end) { d->underrun = 1; return 0; }
+        if (d->cur < d->end) d->low |= d->beg[d->cur];
+        d->range <<= 8;
+        d->cur++;
+    }
+    uint32_t r1 = (d->range * *state) >> 8;
+    d->range -= r1;
+    if (d->low < d->range) { *state = d->zero[*state]; return 0; }
+    d->low -= d->range;
+    d->range = r1;
+    *state = d->one[*state];
+    return 1;
+}
+
+static uint32_t rdec_u(rdec* d, uint8_t* st)   /* rangecoder::u, :105-132 */
+{
+    if (rdec_bin(d, &st[0])) return 0;
+    int e = 0;
+    while (rdec_bin(d, &st[1 + (e < 9 ? e : 9)])) if (++e > 31) { d->underrun = 1; d->range = 0; return 0; }
+    uint32_t a = 1;
+    for (int i = e - 1; i >= 0; i--) a = (a << 1) | (uint32_t)rdec_bin(d, &st[22 + (i < 9 ? i : 9)]);
+    return a;
+}
+
+static int32_t rdec_s(rdec* d, uint8_t* st)    /* rangecoder::s, :135-171 */
+{
+    if (rdec_bin(d, &st[0])) return 0;
+    int e = 0;
+    while (rdec_bin(d, &st[1 + (e < 9 ? e : 9)])) if (++e > 31) { d->underrun = 1; d->range = 0; return 0; }
+    int32_t a = 1;
+    for (int i = e - 1; i >= 0; i--) a = (a << 1) | rdec_bin(d, &st[22 + (i < 9 ? i : 9)]);
+    return rdec_bin(d, &st[11 + (e < 10 ? e : 10)]) ? -a : a;
+}
+
+typedef struct {
+    int bits, num_h, num_v, nsets, ec, intra;
+    int nctx[8];
+    int16_t q[8][5][256];
+    uint8_t one[256];
+} dec_params;
+
+/* 0, or the reference's error text */
+static const char* parse_record(const uint8_t* rec, size_t n, dec_params* P)
+{
+    if (n < 5) return "FFV1-HEADER-END:1";
+    if (ffv1o_crc32(rec, n)) return "FFV1-HEADER-configuration_record_crc_parity:1";
+    uint8_t def[256];
+    ffv1o_default_transitions(def);
+    rdec d;
+    rdec_init(&d, rec, n - 4, def);
+    uint8_t st[32];
+    memset(st, 128, 32);
+    if (rdec_u(&d, st) != 3) return "FFV1-HEADER-version";
+    if (rdec_u(&d, st) < 4) return "FFV1-HEADER-micro_version-EXPERIMENTAL:1";
+    uint32_t coder = rdec_u(&d, st);
+    if (coder == 0 || coder > 2) return "FFV1-HEADER-coder_type:1";
+    memcpy(P->one, def, 256);
+    if (coder == 2)
+        for (int i = 1; i < 256; i++) {
+            int v = def[i] + rdec_s(&d, st);
+            if (v < 0 || v > 255) return "FFV1-HEADER-state_transition_delta:1";
+            P->one[i] = (uint8_t)v;
+        }
+    if (rdec_u(&d, st) != 1) return "colorspace_type";
+    P->bits = (int)rdec_u(&d, st);
+    if (!P->bits) P->bits = 8;
+    if (!rdec_bin(&d, &st[0])) return "chroma_planes";
+    if (rdec_u(&d, st) || rdec_u(&d, st)) return "chroma subsampling";
+    if (rdec_bin(&d, &st[0])) return "alpha_plane";
+    P->num_h = (int)rdec_u(&d, st) + 1;
+    P->num_v = (int)rdec_u(&d, st) + 1;
+    P->nsets = (int)rdec_u(&d, st);
+    if (P->nsets < 1 || P->nsets > 8) return "FFV1-HEADER-quant_table_count:1";
+    for (int s = 0; s < P->nsets; s++) {
+        int scale = 1;
+        for (int t = 0; t < 5; t++) {          /* parameters::QuantizationTable, FFV1_Parameters.cpp:222-253 */
+            uint8_t qs[32];
+            memset(qs, 128, 32);
+            int v = 0;
+            for (int k = 0; k < 128;) {
+                uint32_t len_minus1 = rdec_u(&d, qs);
+                if (k + len_minus1 >= 128 || d.underrun) return "FFV1-HEADER-QuantizationTable-len:1";
+                for (uint32_t a = 0; a <= len_minus1; a++) P->q[s][t][k++] = (int16_t)(scale * v);
+                v++;
+            }
+            for (int k = 1; k < 128; k++) P->q[s][t][256 - k] = (int16_t)-P->q[s][t][k];
+            P->q[s][t][128] = (int16_t)-P->q[s][t][127];
+            scale *= 2 * v - 1;
+            if (scale > 32768) return "FFV1-HEADER-QuantizationTable-scale:1";
+        }
+        P->nctx[s] = (scale + 1) >> 1;
+    }
+    for (int s = 0; s < P->nsets; s++) if (rdec_bin(&d, &st[0])) return "states_coded";
+    P->ec = (int)rdec_u(&d, st);
+    if (P->ec > 1) return "FFV1-HEADER-ec:1";
+    P->intra = (int)rdec_u(&d, st);
+    return d.underrun ? "FFV1-HEADER-END:1" : 0;
+}
+
+/* inverse of load_rgb: writes pixel (x, y) into the payload (Transform.cpp:70-420) */
+static void store_rgb(uint8_t* p, uint32_t w, int layout, uint32_t x, uint32_t y, uint32_t r, uint32_t g, uint32_t b)
+{
+    uint8_t* row = p + ffv1o_row_bytes(w, layout) * y;
+    switch (layout) {
+    case L_DPX_RGB_8: case L_TIFF_RGB_8:
+        row[3 * x] = (uint8_t)r; row[3 * x + 1] = (uint8_t)g; row[3 * x + 2] = (uint8_t)b; break;
+    case L_DPX_RGB_10_FA_LE: case L_DPX_RGB_10_FA_BE: {
+        uint32_t v = r << 22 | g << 12 | b << 2;
+        uint8_t* q = row + 4 * x;
+        if (layout == L_DPX_RGB_10_FA_BE) { q[0] = (uint8_t)(v >> 24); q[1] = (uint8_t)(v >> 16); q[2] = (uint8_t)(v >> 8); q[3] = (uint8_t)v; }
+        else { q[3] = (uint8_t)(v >> 24); q[2] = (uint8_t)(v >> 16); q[1] = (uint8_t)(v >> 8); q[0] = (uint8_t)v; }
+        break; }
+    case L_DPX_RGB_12_FA_LE: case L_DPX_RGB_16_LE: case L_TIFF_RGB_16_LE: case L_DPX_RGB_12_FA_BE: case L_DPX_RGB_16_BE: case L_TIFF_RGB_16_BE: {
+        int sh = (layout == L_DPX_RGB_12_FA_LE || layout == L_DPX_RGB_12_FA_BE) ? 4 : 0;
+        int be = layout == L_DPX_RGB_12_FA_BE || layout == L_DPX_RGB_16_BE || layout == L_TIFF_RGB_16_BE;
+        uint32_t c[3] = { r << sh, g << sh, b << sh };
+        uint8_t* q = row + 6 * x;
+        for (int i = 0; i < 3; i++) {
+            if (be) { q[2 * i] = (uint8_t)(c[i] >> 8); q[2 * i + 1] = (uint8_t)c[i]; }
+            else { q[2 * i + 1] = (uint8_t)(c[i] >> 8); q[2 * i] = (uint8_t)c[i]; }
+        }
+        break; }
+    case L_DPX_RGB_12_PACKED_BE: {
+        uint32_t c[3] = { r, g, b };
+        for (int i = 0; i < 3; i++) {
+            size_t bit = ((size_t)x * 3 + i) * 12;
+            for (int k = 0; k < 12; k++) {
+                size_t bb = bit + k;
+                uint8_t* q = row + (bb / 32) * 4 + (3 - (bb % 32) / 8);   /* bit bb % 32 of a big-endian word */
+                if ((c[i] >> k) & 1u) *q |= (uint8_t)(1u << (bb % 8)); else *q &= (uint8_t)~(1u << (bb % 8));
+            }
+        }
+        break; }
+    }
+}
+
+/* flags as in include/b200dec.h: 1 tail, 2 crc, 4 header, 8 underrun, 16 junk, 32 error_status. Returns 0 when the call worked
+ * (the record parsed, the output buffer was large enough), else -1; *flags tells about the stream. Row padding is written as zeros. */
+int ffv1o_decode_frame(const uint8_t* rec, size_t rec_len, uint32_t w, uint32_t h, int layout,
+                       const uint8_t* pkt, size_t pkt_len, uint8_t* out, size_t out_cap, uint32_t* flags)
+{
+    dec_params* P = (dec_params*)malloc(sizeof(dec_params));
+    *flags = 0;
+    if (!P || parse_record(rec, rec_len, P) || P->bits != ffv1o_layout_bits(layout) || ffv1o_frame_bytes(w, h, layout) > out_cap) { free(P); return -1; }
+    memset(out, 0, ffv1o_frame_bytes(w, h, layout));
+    const size_t tail = P->ec ? 8 : 3;
+    const int bits_max = P->bits + 1, off = 1 << P->bits, mask = (1 << bits_max) - 1;
+    const int swap_bg = P->bits > 8 && P->bits < 16;          /* Transform.cpp:104,126,233,338,363 */
+    int maxctx = 0;
+    for (int s = 0; s < P->nsets; s++) if (P->nctx[s] > maxctx) maxctx = P->nctx[s];
+    uint8_t* states = (uint8_t*)malloc((size_t)2 * maxctx * 32);
+    size_t pos = pkt_len;
+    int nslices = 0;
+    while (pos) {                                             /* FFV1_Frame.cpp:166-197: slices from the end of the packet */
+        if (pos < tail || nslices >= P->num_h * P->num_v) { *flags |= 1; break; }
+        size_t size = ((size_t)pkt[pos - tail] << 16 | (size_t)pkt[pos - tail + 1] << 8 | pkt[pos - tail + 2]) + tail;
+        if (size > pos) { *flags |= 1; break; }
+        pos -= size;
+        nslices++;
+        const uint8_t* sp = pkt + pos;
+        if (P->ec && ffv1o_crc32(sp, size)) *flags |= 2;      /* FFV1_Slice.cpp:247-249; decoding goes on */
+        rdec d;
+        rdec_init(&d, sp, size - tail, P->one);
+        if (pos == 0) {                                       /* first slice: the keyframe bin, FFV1_Slice.cpp:221-225 */
+            uint8_t key = 128;
+            if (!rdec_bin(&d, &key)) { *flags |= 4; continue; }
+        }
+        uint8_t hs[32];
+        memset(hs, 128, 32);
+        uint32_t sx = rdec_u(&d, hs), sy = rdec_u(&d, hs), sw1 = rdec_u(&d, hs), sh1 = rdec_u(&d, hs);
+        uint32_t qi[2] = { rdec_u(&d, hs), 0 };
+        qi[1] = rdec_u(&d, hs);
+        rdec_u(&d, hs); rdec_u(&d, hs); rdec_u(&d, hs);       /* picture_structure, sar_num, sar_den */
+        uint32_t x2 = sx + sw1 + 1, y2 = sy + sh1 + 1;
+        if (sx >= (uint32_t)P->num_h || sy >= (uint32_t)P->num_h || x2 > (uint32_t)P->num_h || y2 > (uint32_t)P->num_v ||
+            qi[0] >= (uint32_t)P->nsets || qi[1] >= (uint32_t)P->nsets || d.underrun) { *flags |= 4; continue; }
+        const uint32_t gx = (uint32_t)((uint64_t)sx * w / P->num_h), gy = (uint32_t)((uint64_t)sy * h / P->num_v);
+        const uint32_t gw = (uint32_t)((uint64_t)x2 * w / P->num_h) - gx, gh = (uint32_t)((uint64_t)y2 * h / P->num_v) - gy;
+        memset(states, 128, (size_t)2 * maxctx * 32);         /* keyframe: every state back to 128, FFV1_Coder_RangeCoder.cpp:25-48 */
+        /* two rows per plane with 2 samples of margin on the left and 1 on the right (FFV1_Slice.cpp:406-444) */
+        int32_t* buf = (int32_t*)calloc((size_t)3 * 2 * (gw + 3), sizeof(int32_t));
+        int32_t* sample[3][2];
+        for (int c = 0; c < 3; c++) { sample[c][0] = buf + (size_t)2 * c * (gw + 3) + 2; sample[c][1] = sample[c][0] + gw + 3; }
+        for (uint32_t y = 0; y < gh; y++) {
+            for (int c = 0; c < 3; c++) {
+                int32_t* t = sample[c][0]; sample[c][0] = sample[c][1]; sample[c][1] = t;      /* swap */
+                sample[c][1][-1] = sample[c][0][0];
+                sample[c][0][gw] = sample[c][0][gw - 1];
+                const int ps = (c + 1) >> 1;
+                const int16_t (*Q)[256] = P->q[qi[ps]];
+                const int is5 = Q[3][127] != 0;
+                uint8_t* S = states + (size_t)ps * maxctx * 32;
+                int32_t *s0 = sample[c][0], *s1 = sample[c][1];   /* previous row, current row (Line, :447-472) */
+                for (uint32_t x = 0; x < gw; x++) {
+                    const int LT = s0[(int)x - 1], T = s0[x], RT = s0[x + 1], L = s1[(int)x - 1];
+                    int ctx = Q[0][(L - LT) & 255] + Q[1][(LT - T) & 255] + Q[2][(T - RT) & 255];
+                    if (is5) ctx += Q[3][(s1[(int)x - 2] - L) & 255] + Q[4][(s1[x] - T) & 255];   /* LL, TT (row y-2 still in place) */
+                    int pred = median3(L, L + T - LT, T);
+                    int32_t v = ctx >= 0 ? pred + rdec_s(&d, S + (size_t)ctx * 32) : pred - rdec_s(&d, S + (size_t)(-ctx) * 32);
+                    s1[x] = v & mask;
+                }
+            }
+            for (uint32_t x = 0; x < gw; x++) {               /* JPEG2000RCT, Transform.cpp:29-37 */
+                int32_t g = sample[0][1][x], b = sample[1][1][x] - off, r = sample[2][1][x] - off;
+                g -= (b + r) >> 2; b += g; r += g;
+                if (swap_bg) { int32_t t = g; g = b; b = t; }
+                store_rgb(out, w, layout, gx + x, gy + y, (uint32_t)r & (uint32_t)(off - 1), (uint32_t)g & (uint32_t)(off - 1), (uint32_t)b & (uint32_t)(off - 1));
+            }
+        }
+        free(buf);
+        uint8_t endst = 129;                                  /* terminator, FFV1_Slice.cpp:335-341 */
+        rdec_bin(&d, &endst);
+        const size_t adj = d.range < 0x100 ? 0 : 1;
+        if (d.underrun || d.cur - adj > d.end) *flags |= 8;
+        const size_t used = d.cur > d.end ? d.end : d.cur - adj;
+        if (used < d.end) *flags |= 16;
+        if (P->ec && sp[size - 5]) *flags |= 32;
+    }
+    if (nslices != P->num_h * P->num_v) *flags |= 1;
+    free(states);
+    free(P);
+    return 0;
 }

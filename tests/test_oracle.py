@@ -88,3 +88,53 @@ def test_oracle_bins_consistent():
     assert sizes.sum() == len(pkt)
     total = sum(len(util.oracle_slice_bins(payload, w, h, layout, 2, 2, sx, sy)) for sy in range(2) for sx in range(2))
     assert total == bins
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# decoder restatement (oracle/ffv1_oracle.c, second half): pinned to the unmodified reference decoder and to the sources
+@pytest.mark.parametrize("i", range(NGOLD))
+def test_oracle_decoder_on_ffmpeg_golden(i):
+    w, h, layout, slices, context, ec, payload, rec, pkt = util.golden_case(i)
+    got, flags = util.oracle_decode(rec, pkt, w, h, layout)
+    assert flags == 0
+    if util.ref_available():
+        assert got == util.ref_decode(rec, pkt, w, h, layout)
+    src = np.ascontiguousarray(payload, np.uint8).reshape(-1)
+    rb = S.row_bytes(w, layout)
+    valid = {S.DPX_RGB_8: 3 * w, S.DPX_RGB_16_LE: 6 * w, S.DPX_RGB_16_BE: 6 * w}.get(layout, rb)
+    a = np.frombuffer(got, np.uint8).reshape(h, rb)[:, :valid]
+    assert np.array_equal(a, src.reshape(h, rb)[:, :valid])
+
+
+@pytest.mark.parametrize("layout", sorted(S.LAYOUT_BITS))
+def test_oracle_decoder_inverts_oracle_encoder(layout):
+    for (w, h, slices) in ((48, 36, 4), (70, 50, 6), (33, 31, 4)):
+        for context, ec in ((1, 1), (0, 0)):
+            nh, nv = util.oracle_grid(w, h, slices, S.LAYOUT_BITS[layout])
+            rec = util.oracle_record(w, h, layout, nh, nv, context, ec)
+            for kind in ("grain", "white", "const"):
+                f = S.synth_payload(w, h, layout, 90, kind)
+                pkt = util.oracle_encode(f, w, h, layout, nh, nv, context, ec)
+                got, flags = util.oracle_decode(rec, pkt, w, h, layout)
+                assert flags == 0 and got == np.asarray(f, np.uint8).tobytes(), (layout, w, h, context, ec, kind)
+
+
+def test_oracle_decoder_flags_damage():
+    w, h, layout = 70, 50, S.DPX_RGB_16_BE
+    nh, nv = util.oracle_grid(w, h, 6, 16)
+    rec = util.oracle_record(w, h, layout, nh, nv)
+    f = S.synth_payload(w, h, layout, 91)
+    pkt = bytearray(util.oracle_encode(f, w, h, layout, nh, nv))
+    bad = bytearray(pkt)
+    bad[len(bad) // 2] ^= 1
+    got, flags = util.oracle_decode(rec, bytes(bad), w, h, layout)
+    assert flags & 2 and got != np.asarray(f, np.uint8).tobytes()          # slice CRC
+    got, flags = util.oracle_decode(rec, bytes(pkt[:-5]), w, h, layout)
+    assert flags & 1                                                         # tail walk
+    bad = bytearray(pkt)
+    bad[0] ^= 0x80                                                           # the keyframe bin
+    if util.ref_available():
+        with pytest.raises(RuntimeError):
+            util.ref_decode(rec, bytes(bad), w, h, layout)
+    _, flags = util.oracle_decode(rec, bytes(bad), w, h, layout)
+    assert flags != 0

@@ -37,6 +37,9 @@ def oracle():
         O.ffv1o_crc32.restype = C.c_uint32
         O.ffv1o_crc32.argtypes = [C.c_void_p, C.c_size_t]
         O.ffv1o_slice_grid.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        O.ffv1o_decode_frame.restype = C.c_int
+        O.ffv1o_decode_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_uint32)]
         _oracle = O
     return _oracle
 
@@ -69,6 +72,17 @@ def oracle_encode(payload, width, height, layout, num_h, num_v, context=1, ec=1,
     if want_sizes:
         return pkt, sizes, bins.value
     return pkt
+
+
+def oracle_decode(record, packet, width, height, layout):
+    """The C restatement of the reference decoder (oracle/ffv1_oracle.c, second half): -> (payload bytes, status flags)."""
+    n = oracle().ffv1o_frame_bytes(width, height, layout)
+    out = np.zeros(n, np.uint8)
+    flags = C.c_uint32(0)
+    rc = oracle().ffv1o_decode_frame(bytes(record), len(record), width, height, layout, bytes(packet), len(packet), out.ctypes.data, n, C.byref(flags))
+    if rc:
+        raise RuntimeError("oracle decoder refused the stream")
+    return out.tobytes(), flags.value
 
 
 def oracle_slice_bins(payload, width, height, layout, num_h, num_v, sx, sy, context=1):
