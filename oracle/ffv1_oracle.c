@@ -20,7 +20,7 @@
  *   CRC                    ZenCRC32                      Source/Lib/Utils/CRC32/ZenCRC32.cpp:1097-1135
  *   pixel layouts + RCT    Transform                     Source/Lib/Transform/Transform.cpp:29-37, :70-420
  *
-* Pinning of the encoder half (tests/test_oracle.py): (1) every packet decodes through the UNMODIFIED reference decoder
+ * Pinning of the encoder half (tests/test_oracle.py): (1) every packet decodes through the UNMODIFIED reference decoder
  * (oracle/_ref/libref_ffv1dec.so) to the input bytes — the property all of the reference's own tests pin
  * (test1.sh, test2.sh, slices.sh: round trip through `rawcooked --check`); (2) config record and packets
  * are byte-identical to libavcodec 62.11.100's for the golden vectors in tests/golden/.
