@@ -1,6 +1,7 @@
 """GPU parity tests of the decode + compare path (`--check` side, include/b200dec.h), run with -m gpu on a B200.
-The oracle here is the UNMODIFIED reference decoder (oracle/_ref/libref_ffv1dec.so: ffv1_frame::Process + Transform): the
-CUDA decoder, called through the C ABI, must produce the same payload bytes for
+The checkers here are the UNMODIFIED reference decoder (oracle/_ref/libref_ffv1dec.so: ffv1_frame::Process + Transform) and the
+plain-C restatement of it (oracle/ffv1_oracle.c, second half): the CUDA decoder, called through the C ABI, must produce the same
+payload bytes for
   * libavcodec's own packets (tests/golden/ffv1_golden.npz),
   * the CUDA encoder's packets of every layout, ragged grids, both context models, slicecrc 0/1,
 and the on-GPU compare must report 0 for the source payload, the exact number of flipped bytes otherwise, and the
@@ -38,6 +39,7 @@ def test_decoder_on_ffmpeg_golden_packets(i):
             assert np.array_equal(o[m], src[m])
             if want is not None:
                 assert o.tobytes() == want
+            assert (o.tobytes(), 0) == util.oracle_decode(rec, pkt, w, h, layout)      # the C restatement of the decoder
         mm, st = dec.check([pkt, pkt], [src, src])
         assert mm == [0, 0] and st == [0, 0]
     finally:
@@ -66,6 +68,8 @@ def test_decoder_inverts_the_encoder_and_equals_reference(layout, w, h, slices):
                     assert np.array_equal(o[m], np.asarray(f, np.uint8).reshape(-1)[m])
                     if util.ref_available() and spw == 4:
                         assert o.tobytes() == util.ref_decode(rec, p, w, h, layout)
+                    if spw == 1:
+                        assert (o.tobytes(), 0) == util.oracle_decode(rec, p, w, h, layout)
                 mm, st = dec.check(pkts, frames)
                 assert mm == [0] * 4 and st == [0] * 4
             finally:
