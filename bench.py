@@ -436,8 +436,9 @@ def run_b200(args):
     flac_bytes = [0]
 
     def run_e2e(steps):
-        """`steps` batches through the host entry points, two in flight: batch i+1 is submitted (H2D band by band + kernels)
-        before the packets of batch i are fetched (D2H), so both PCIe directions hide behind the kernels."""
+        """`steps` batches through the host entry points, two in flight: while batch i is coded, the frames of batch i+1 go up
+        (b200_ffv1_prefetch_host / b200_ffv1_submit_host) and the packets of batch i-1 come down (b200_ffv1_fetch_packets), so
+        both PCIe directions hide behind the kernels; only the first upload and the last download of a run have nothing to hide behind."""
         submitted = fetched = 0
         for _ in range(min(2, steps)):
             ck(L.b200_ffv1_submit_host(enc._h, ptrs, F))
